@@ -1,0 +1,582 @@
+"""Mechanism code generator: ``pelec_b200/mechanisms/<mech>.json`` -> source code.
+
+Two flavours from the same table:
+
+* ``emit(mech, "cuda")``: a ``__device__`` header for the sm_100a kernels
+  (``pelec_b200/csrc/gen/mech_<mech>.cuh``) - the product.
+* ``emit(mech, "c")``: a plain-C header for the CPU restatement
+  (``oracle/gen/mech_<mech>.h``) - test infrastructure.
+
+What is generated (reference function each one restates; LiDryer line numbers of
+``PP/Mechanisms/LiDryer/mechanism.H``):
+
+  cv_R / cp_R / gibbs / e_RT / h_RT / dcvpRdT   NASA-7 polynomials          (:199/:265/:331/:532/:615/:781)
+  ckcvbs / ckubms / ckcpbs / ckhbms             mixture cv, e, cp, h [CGS]   (:981/:1238/:862/:1100)
+  production_rate(wdot, sc, T)                   molar rates, SI             (:2285-2603)
+  ajacobian(J, sc, T, consP)                     analytic d(wdot,Tdot)/d(C,T)  (:3905-5138)
+
+``production_rate`` keeps the reference's reaction order and arithmetic association so
+that the CPU flavour reproduces the reference bit-for-bit up to libm; the Jacobian is
+derived here from the rate law (same mathematics as the reference's ``aJacobian``, not
+the same text): it only steers Newton convergence, never the converged answer.
+
+Jacobian storage is behind a macro ``PRX_J(row, col)`` = d f_row / d x_col so the kernel
+can choose its own shared-memory layout; default is column-major ``J[col*(N+1)+row]`` as
+in the reference (``J[k*neq+m] = d wdot_m / d C_k``).
+"""
+import json
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MECH_JSON_DIR = os.path.join(HERE, "..", "mechanisms")
+
+
+def load(mech):
+    with open(os.path.join(MECH_JSON_DIR, mech + ".json")) as f:
+        return json.load(f)
+
+
+def lit(s):
+    """A double literal that C parses to the same value as the reference's token."""
+    s = str(s)
+    if not any(c in s for c in ".eE"):
+        s += ".0"
+    return s
+
+
+def signed_sum(terms, var_of):
+    """[[coef, key], ...] -> '+c0*v0 - c1*v1 ...' keeping order and association."""
+    out = []
+    for i, (coef, key) in enumerate(terms):
+        neg = coef.startswith("-")
+        mag = coef[1:] if neg else coef
+        v = var_of(key)
+        body = lit(mag) if v is None else "%s * %s" % (lit(mag), v)
+        if i == 0:
+            out.append(("-" if neg else "") + body)
+        else:
+            out.append((" - " if neg else " + ") + body)
+    return "".join(out)
+
+
+def poly_expr(terms):
+    return signed_sum(terms, lambda b: None if b == "1" else b)
+
+
+class Emitter:
+    def __init__(self, d, flavour):
+        self.d = d
+        self.fl = flavour
+        self.N = len(d["species"])
+        self.L = []
+        self.q = "__device__ __forceinline__ " if flavour == "cuda" else "static inline "
+
+    def w(self, s=""):
+        self.L.append(s)
+
+    # ------------------------------------------------------------------ thermo
+    def thermo_groups(self, fname):
+        """species grouped by Tmid, in ascending Tmid, 'no change' species first."""
+        th = self.d["thermo"][fname]
+        groups = {}
+        for k, t in enumerate(th):
+            groups.setdefault(t["tmid"], []).append(k)
+        keys = sorted(groups, key=lambda x: (-1 if x is None else x))
+        return th, [(k, groups[k]) for k in keys]
+
+    def emit_species_fn(self, name, fname, need):
+        """void name(double* sp, double T): sp[k] = poly_k(T)."""
+        w = self.w
+        th, groups = self.thermo_groups(fname)
+        w("%svoid %s(double* PRX_RESTRICT sp, const double T)" % (self.q, name))
+        w("{")
+        self.emit_T_powers(need)
+        for tmid, ks in groups:
+            if tmid is None:
+                for k in ks:
+                    w("  sp[%d] = %s;" % (k, poly_expr(th[k]["lo"])))
+            else:
+                w("  if (T < %s) {" % lit(int(tmid)))
+                for k in ks:
+                    w("    sp[%d] = %s;" % (k, poly_expr(th[k]["lo"])))
+                w("  } else {")
+                for k in ks:
+                    w("    sp[%d] = %s;" % (k, poly_expr(th[k]["hi"])))
+                w("  }")
+        w("}")
+        w()
+
+    def emit_T_powers(self, need):
+        w = self.w
+        if "T2" in need:
+            w("  const double T2 = T * T;")
+        if "T3" in need:
+            w("  const double T3 = T * T * T;")
+        if "T4" in need:
+            w("  const double T4 = T * T * T * T;")
+        if "invT" in need:
+            w("  const double invT = 1.0 / T;")
+        if "logT" in need:
+            w("  const double logT = log(T);")
+
+    def emit_mix_fn(self, name, fname, need, scale_RT):
+        """double name(T, y): (sum_k y_k * poly_k(T) * imw_k) * (Ru*T | Ru)."""
+        w = self.w
+        th, groups = self.thermo_groups(fname)
+        imw = self.d["imw"]
+        w("%sdouble %s(const double T, const double* PRX_RESTRICT y)" % (self.q, name))
+        w("{")
+        w("  double result = 0.0;")
+        self.emit_T_powers(need)
+        for tmid, ks in groups:
+            if tmid is None:
+                for k in ks:
+                    w("  result += y[%d] * (%s) * %s;" % (k, poly_expr(th[k]["lo"]), imw[k]))
+            else:
+                w("  if (T < %s) {" % lit(int(tmid)))
+                for k in ks:
+                    w("    result += y[%d] * (%s) * %s;" % (k, poly_expr(th[k]["lo"]), imw[k]))
+                w("  } else {")
+                for k in ks:
+                    w("    result += y[%d] * (%s) * %s;" % (k, poly_expr(th[k]["hi"]), imw[k]))
+                w("  }")
+        if scale_RT:
+            w("  const double RT = %s * T;" % self.d["Ru"])
+            w("  return result * RT;")
+        else:
+            w("  return result * %s;" % self.d["Ru"])
+        w("}")
+        w()
+
+    # ------------------------------------------------------------------ kinetics helpers
+    @staticmethod
+    def arrh(A, beta, Ea, style="ref"):
+        """A * exp((beta) * logT - (Ea) * invT) with the reference's variants."""
+        if beta is None and Ea is None:
+            return lit(A)
+        if beta is not None and Ea is not None:
+            return "%s * exp((%s) * logT - (%s) * invT)" % (lit(A), beta, Ea)
+        if beta is not None:
+            return "%s * exp((%s) * logT)" % (lit(A), beta)
+        return "%s * exp(-(%s) * invT)" % (lit(A), Ea)
+
+    @staticmethod
+    def conc_product(idx, var="sc"):
+        return " * ".join("%s[%d]" % (var, i) for i in idx)
+
+    @staticmethod
+    def corr_expr(eff):
+        s = "mixture"
+        for i, c in eff:
+            if c == "1":
+                s += " + sc[%d]" % i
+            else:
+                s += " + (%s) * sc[%d]" % (lit(c), i)
+        return s
+
+    @staticmethod
+    def low_expr(low):
+        A0, b0, E0 = low["A"], low["beta"], low["Ea"]
+        if b0 is not None and E0 is not None:
+            return "%s * exp(%s * logT - %s * invT)" % (lit(A0), b0, E0)
+        if E0 is not None:
+            return "%s * exp(-%s * invT)" % (lit(A0), E0)
+        return "%s * exp(%s * logT)" % (lit(A0), b0)
+
+    @staticmethod
+    def fcent_expr(fc):
+        parts = []
+        for a, x in fc["exp_terms"]:
+            neg = a.startswith("-")
+            mag = a[1:] if neg else a
+            t = "%s * exp(-T * %s)" % (lit(mag), lit(x))
+            parts.append((neg, t))
+        if fc["invT_coef"] is not None:
+            parts.append((False, "exp(%s * invT)" % fc["invT_coef"]))
+        if fc["const"] is not None:
+            parts.append((False, lit(fc["const"])))
+        s = ""
+        for i, (neg, t) in enumerate(parts):
+            if i == 0:
+                s = ("-" if neg else "") + t
+            else:
+                s += (" - " if neg else " + ") + t
+        return s
+
+    @staticmethod
+    def dg_expr(dG, var="g_RT"):
+        return signed_sum([[c, k] for c, k in dG],
+                          lambda k: None)  # placeholder, replaced below
+
+    def dg_sum(self, dG, var):
+        out = ""
+        for i, (c, k) in enumerate(dG):
+            neg = c.startswith("-")
+            mag = c[1:] if neg else c
+            t = "%s[%d]" % (var, k) if mag == "1" else "%s * %s[%d]" % (lit(mag), var, k)
+            if i == 0:
+                out = ("-" if neg else "") + t
+            else:
+                out += (" - " if neg else " + ") + t
+        return out
+
+    @staticmethod
+    def refc_factor(p):
+        return {0: None, 1: "refC", -1: "refCinv", 2: "(refC * refC)", -2: "(refCinv * refCinv)"}[p]
+
+    # ------------------------------------------------------------------ production rate
+    def emit_production_rate(self):
+        w = self.w
+        d = self.d
+        N = self.N
+        w("// molar production rates [mol/m^3/s] from concentrations sc [mol/m^3] and T [K]")
+        w("%svoid production_rate(double* PRX_RESTRICT wdot, const double* PRX_RESTRICT sc, const double T)" % self.q)
+        w("{")
+        w("  const double invT = 1.0 / T;")
+        w("  const double logT = log(T);")
+        w("  const double refC = %s / %s * invT;" % (lit(d["refC_num"]), d["refC_den"]))
+        w("  const double refCinv = 1 / refC;")
+        w("  for (int i = 0; i < %d; ++i) wdot[i] = 0.0;" % N)
+        w("  double mixture = 0.0;")
+        w("  for (int i = 0; i < %d; ++i) mixture += sc[i];" % N)
+        w("  double g_RT[%d];" % N)
+        w("  gibbs(g_RT, T);")
+        w("  (void)refC; (void)refCinv; (void)mixture;")
+        for r in d["reactions"]:
+            w("  { // R%d: %s" % (r["idx"], r["eq"]))
+            w("    const double k_f = %s;" % self.arrh(r["A"], r["beta"], r["Ea"]))
+            pre = ""
+            if r["type"] in ("three_body", "falloff"):
+                w("    double Corr = %s;" % self.corr_expr(r["eff"]))
+                pre = "Corr * "
+            if r["type"] == "falloff":
+                w("    const double redP = Corr / k_f * %s;" % self.low_expr(r["low"]))
+                if r["falloff"] == "troe":
+                    w("    const double F = redP / (1.0 + redP);")
+                    w("    const double logPred = log10(redP);")
+                    w("    const double logFcent = log10(%s);" % self.fcent_expr(r["fcent"]))
+                    w("    const double troe_c = -0.4 - 0.67 * logFcent;")
+                    w("    const double troe_n = 0.75 - 1.27 * logFcent;")
+                    w("    const double troe = (troe_c + logPred) / (troe_n - 0.14 * (troe_c + logPred));")
+                    w("    const double F_troe = exp(PRX_LN10 * logFcent / (1.0 + troe * troe));")
+                    w("    Corr = F * F_troe;")
+                else:
+                    w("    Corr = redP / (1.0 + redP);")
+            w("    const double qf = %sk_f * (%s);" % (pre, self.conc_product(r["reactants"])))
+            if r["reversible"]:
+                rc = self.refc_factor(r["refC"])
+                rcs = "" if rc is None else ("%s * " % (rc if rc.startswith("(") else "(" + rc + ")"))
+                w("    const double qr = %sk_f * exp(-(%s)) * %s(%s);" % (
+                    pre, self.dg_sum(r["dG"], "g_RT"), rcs, self.conc_product(r["products"])))
+            else:
+                w("    const double qr = 0.0;")
+            w("    const double qdot = qf - qr;")
+            for k, c in r["wdot"]:
+                neg = c.startswith("-")
+                mag = c[1:] if neg else c
+                if mag == "1":
+                    w("    wdot[%d] %s qdot;" % (k, "-=" if neg else "+="))
+                else:
+                    w("    wdot[%d] %s %s * qdot;" % (k, "-=" if neg else "+=", lit(mag)))
+            w("  }")
+        w("}")
+        w()
+
+    # ------------------------------------------------------------------ analytic Jacobian
+    def emit_ajacobian(self):
+        """d(wdot_m)/d(C_k), d(wdot_m)/dT, d(Tdot)/d(C_k), d(Tdot)/dT; SI concentrations.
+
+        Derivation (per reaction, q = Corr * (kf*Pf - kr*Pr), kr = kf*Kinv):
+          dln(kf)/dT   = beta/T + Ea/T^2
+          dln(Kinv)/dT = (sum_k c_k h_RT_k - p)/T        (Kinv = exp(-sum c_k g_k) refC^p)
+          three-body   : Corr = alpha = sum_k (1+eff_k) C_k
+          falloff      : Pr = alpha k0/kf ; Corr = Pr/(1+Pr) * F_troe(T, Pr)
+        """
+        w = self.w
+        d = self.d
+        N = self.N
+        neq = N + 1
+        w("// analytic Jacobian, SI concentrations; PRX_J(row, col) = d f_row / d x_col,")
+        w("// rows/cols 0..N-1 species (wdot_m, C_k), N = temperature (Tdot, T).")
+        w("%svoid ajacobian(double* PRX_RESTRICT J, const double* PRX_RESTRICT sc, const double T, const int consP)" % self.q)
+        w("{")
+        w("  for (int i = 0; i < %d; ++i) for (int j = 0; j < %d; ++j) PRX_J(i, j) = 0.0;" % (neq, neq))
+        w("  double wdot[%d];" % N)
+        w("  for (int i = 0; i < %d; ++i) wdot[i] = 0.0;" % N)
+        w("  const double invT = 1.0 / T;")
+        w("  const double invT2 = invT * invT;")
+        w("  const double logT = log(T);")
+        w("  const double refC = %s / %s / T;" % (lit(d["refC_num"]), d["refC_den"]))
+        w("  const double refCinv = 1.0 / refC;")
+        w("  double mixture = 0.0;")
+        w("  for (int k = 0; k < %d; ++k) mixture += sc[k];" % N)
+        w("  double g_RT[%d], h_RT[%d];" % (N, N))
+        w("  gibbs(g_RT, T);")
+        w("  h_RT_fn(h_RT, T);")
+        w("  const double ln10 = PRX_LN10;")
+        w("  const double log10e = 1.0 / PRX_LN10;")
+        w("  (void)refC; (void)refCinv; (void)mixture; (void)ln10; (void)log10e; (void)invT2; (void)logT;")
+        w("  double dqdc[%d];" % N)
+        w("  for (int k = 0; k < %d; ++k) dqdc[k] = 0.0;" % N)
+        for r in d["reactions"]:
+            w("  { // R%d: %s" % (r["idx"], r["eq"]))
+            # forward
+            w("    const double phi_f = %s;" % self.conc_product(r["reactants"]))
+            w("    double k_f = %s;" % self.arrh(r["A"], r["beta"], r["Ea"]))
+            dl = []
+            if r["beta"] is not None:
+                dl.append("(%s) * invT" % r["beta"])
+            if r["Ea"] is not None:
+                dl.append("(%s) * invT2" % r["Ea"])
+            w("    const double dlnkfdT = %s;" % (" + ".join(dl) if dl else "0.0"))
+            # reverse
+            if r["reversible"]:
+                rc = self.refc_factor(r["refC"])
+                w("    const double phi_r = %s;" % self.conc_product(r["products"]))
+                w("    const double Kinv = %sexp(-(%s));" % ((rc + " * ") if rc else "", self.dg_sum(r["dG"], "g_RT")))
+                w("    double k_r = k_f * Kinv;")
+                w("    const double dlnKinvdT = invT * ((%s) - %s);" % (self.dg_sum(r["dG"], "h_RT"), lit(r["refC"])))
+                w("    const double dkrdT = (dlnkfdT + dlnKinvdT) * k_r;")
+            else:
+                w("    const double phi_r = 0.0; double k_r = 0.0; const double dkrdT = 0.0;")
+            w("    const double q_nocor = k_f * phi_f - k_r * phi_r;")
+            typ = r["type"]
+            if typ == "elementary":
+                w("    const double q = q_nocor;")
+                w("    const double dqdT = dlnkfdT * k_f * phi_f - dkrdT * phi_r;")
+            elif typ == "three_body":
+                w("    const double alpha = %s;" % self.corr_expr(r["eff"]))
+                w("    const double q = alpha * q_nocor;")
+                w("    const double dqdT = alpha * (dlnkfdT * k_f * phi_f - dkrdT * phi_r);")
+                w("    const double dcdc_fac = q_nocor;")
+                w("    k_f *= alpha; k_r *= alpha;")
+            else:
+                low = r["low"]
+                w("    const double alpha = %s;" % self.corr_expr(r["eff"]))
+                w("    const double k_0 = %s;" % self.low_expr(low))
+                w("    const double Pr = alpha / k_f * k_0;")
+                w("    const double fPr = Pr / (1.0 + Pr);")
+                dl0 = []
+                if low["beta"] is not None:
+                    dl0.append("(%s) * invT" % low["beta"])
+                if low["Ea"] is not None:
+                    dl0.append("(%s) * invT2" % low["Ea"])
+                w("    const double dlnk0dT = %s;" % (" + ".join(dl0) if dl0 else "0.0"))
+                w("    const double dlogPrdT = log10e * (dlnk0dT - dlnkfdT);")
+                w("    const double dlogfPrdT = dlogPrdT / (1.0 + Pr);")
+                if r["falloff"] == "troe":
+                    fc = r["fcent"]
+                    w("    const double logPr = log10(Pr);")
+                    terms = []
+                    dterms = []
+                    for i, (a, x) in enumerate(fc["exp_terms"]):
+                        w("    const double Fc%d = (%s) * exp(-T * %s);" % (i, lit(a), lit(x)))
+                        terms.append("Fc%d" % i)
+                        dterms.append("-Fc%d * %s" % (i, lit(x)))
+                    if fc["invT_coef"] is not None:
+                        w("    const double FcT = exp(%s * invT);" % fc["invT_coef"])
+                        terms.append("FcT")
+                        dterms.append("-FcT * (%s) * invT2" % fc["invT_coef"])
+                    if fc["const"] is not None:
+                        terms.append(lit(fc["const"]))
+                    w("    const double Fcent = %s;" % " + ".join(terms))
+                    w("    const double logFcent = log10(Fcent);")
+                    w("    const double troe_c = -0.4 - 0.67 * logFcent;")
+                    w("    const double troe_n = 0.75 - 1.27 * logFcent;")
+                    w("    const double troePr_den = 1.0 / (troe_n - 0.14 * (troe_c + logPr));")
+                    w("    const double troePr = (troe_c + logPr) * troePr_den;")
+                    w("    const double troe = 1.0 / (1.0 + troePr * troePr);")
+                    w("    const double F = exp(ln10 * logFcent * troe);")
+                    w("    const double dlogFcentdT = log10e / Fcent * (%s);" % " + ".join("(%s)" % t for t in dterms))
+                    w("    const double dlogFdcn_fac = 2.0 * logFcent * troe * troe * troePr * troePr_den;")
+                    w("    const double dlogFdc = -troe_n * dlogFdcn_fac * troePr_den;")
+                    w("    const double dlogFdn = dlogFdcn_fac * troePr;")
+                    w("    const double dlogFdlogPr = dlogFdc;")
+                    w("    const double dlogFdT = dlogFcentdT * (troe - 0.67 * dlogFdc - 1.27 * dlogFdn) + dlogFdlogPr * dlogPrdT;")
+                else:
+                    w("    const double F = 1.0; const double dlogFdlogPr = 0.0; const double dlogFdT = 0.0;")
+                w("    const double Corr = fPr * F;")
+                w("    const double q = Corr * q_nocor;")
+                w("    const double dlnCorrdT = ln10 * (dlogfPrdT + dlogFdT);")
+                w("    const double dqdT = Corr * (dlnkfdT * k_f * phi_f - dkrdT * phi_r) + dlnCorrdT * q;")
+                w("    const double dcdc_fac = q / alpha * (1.0 / (Pr + 1.0) + dlogFdlogPr);")
+                w("    k_f *= Corr; k_r *= Corr;")
+            # stoichiometry
+            nu = {}
+            for k, c in r["wdot"]:
+                nu[k] = nu.get(k, 0.0) + float(c)
+            for k, c in sorted(nu.items()):
+                w("    wdot[%d] += (%s) * q;" % (k, lit(repr(c))))
+            # dq/dC_k, direct part
+            direct = {}
+
+            def powers(lst):
+                p = {}
+                for i in lst:
+                    p[i] = p.get(i, 0) + 1
+                return p
+
+            pf = powers(r["reactants"])
+            pr = powers(r["products"]) if r["reversible"] else {}
+            for k, n in pf.items():
+                others = []
+                for i, m in pf.items():
+                    others += ["sc[%d]" % i] * (m - 1 if i == k else m)
+                e = "%sk_f%s" % ("%d.0 * " % n if n > 1 else "", "".join(" * " + o for o in others))
+                direct.setdefault(k, []).append("+ " + e)
+            for k, n in pr.items():
+                others = []
+                for i, m in pr.items():
+                    others += ["sc[%d]" % i] * (m - 1 if i == k else m)
+                e = "%sk_r%s" % ("%d.0 * " % n if n > 1 else "", "".join(" * " + o for o in others))
+                direct.setdefault(k, []).append("- " + e)
+            rows = sorted(nu.items())
+            if typ == "elementary":
+                for k in sorted(direct):
+                    w("    { const double dqdc = %s;" % " ".join(direct[k]).lstrip("+ "))
+                    for m, c in rows:
+                        w("      PRX_J(%d, %d) += (%s) * dqdc;" % (m, k, lit(repr(c))))
+                    w("    }")
+            else:
+                eff = {}
+                for i, c in r["eff"]:
+                    eff[i] = eff.get(i, 0.0) + float(c)
+                w("    if (consP) {")
+                ks = sorted(set(direct) | set(eff))
+                for k in ks:
+                    parts = []
+                    if k in eff:
+                        parts.append("(%s) * dcdc_fac" % lit(repr(eff[k])))
+                    if k in direct:
+                        parts.append(" ".join(direct[k]))
+                    expr = " ".join(parts).lstrip("+ ")
+                    w("      { const double dqdc = %s;" % expr)
+                    for m, c in rows:
+                        w("        PRX_J(%d, %d) += (%s) * dqdc;" % (m, k, lit(repr(c))))
+                    w("      }")
+                w("    } else {")
+                # NOTE (reference quirk, reproduced on purpose): CEPTR omits the assignment of
+                # dqdc[k] when species k has third-body efficiency 0 and no direct term, so the
+                # reference's loop below adds the STALE dqdc[k] left by an earlier reaction
+                # (e.g. drm19 mechanism.H aJacobian "reaction 80: HCO + M": dqdc[5] missing).
+                # dqdc lives at function scope for that reason.
+                for k in range(N):
+                    tot = 1.0 + eff.get(k, 0.0)
+                    parts = []
+                    if tot != 0.0:
+                        parts.append("dcdc_fac" if tot == 1.0 else "(%s) * dcdc_fac" % lit(repr(tot)))
+                    if k in direct:
+                        parts.append(" ".join(direct[k]))
+                    if not parts:
+                        continue
+                    w("      dqdc[%d] = %s;" % (k, " ".join(parts).lstrip("+ ")))
+                w("      for (int k = 0; k < %d; ++k) {" % N)
+                for m, c in rows:
+                    w("        PRX_J(%d, k) += (%s) * dqdc[k];" % (m, lit(repr(c))))
+                w("      }")
+                w("    }")
+            for m, c in rows:
+                w("    PRX_J(%d, %d) += (%s) * dqdT;" % (m, N, lit(repr(c))))
+            w("  }")
+        # temperature row
+        w("  double c_R[%d], dcRdT[%d], eh_RT[%d];" % (N, N, N))
+        w("  if (consP) { cp_R(c_R, T); for (int k = 0; k < %d; ++k) eh_RT[k] = h_RT[k]; }" % N)
+        w("  else { cv_R(c_R, T); e_RT_fn(eh_RT, T); }")
+        w("  dcvpRdT(dcRdT, T);")
+        w("  double cmix = 0.0, ehmix = 0.0, dcmixdT = 0.0, dehmixdT = 0.0;")
+        w("  for (int k = 0; k < %d; ++k) {" % N)
+        w("    cmix += c_R[k] * sc[k];")
+        w("    dcmixdT += dcRdT[k] * sc[k];")
+        w("    ehmix += eh_RT[k] * wdot[k];")
+        w("    dehmixdT += invT * (c_R[k] - eh_RT[k]) * wdot[k] + eh_RT[k] * PRX_J(k, %d);" % N)
+        w("  }")
+        w("  const double cmixinv = 1.0 / cmix;")
+        w("  const double tmp1 = ehmix * cmixinv;")
+        w("  const double tmp3 = cmixinv * T;")
+        w("  const double tmp2 = tmp1 * tmp3;")
+        w("  for (int k = 0; k < %d; ++k) {" % N)
+        w("    double dehmixdc = 0.0;")
+        w("    for (int m = 0; m < %d; ++m) dehmixdc += eh_RT[m] * PRX_J(m, k);" % N)
+        w("    PRX_J(%d, k) = tmp2 * c_R[k] - tmp3 * dehmixdc;" % N)
+        w("  }")
+        w("  PRX_J(%d, %d) = -tmp1 + tmp2 * dcmixdT - tmp3 * dehmixdT;" % (N, N))
+        w("}")
+        w()
+
+    # ------------------------------------------------------------------ whole file
+    def emit(self):
+        d = self.d
+        N = self.N
+        w = self.w
+        guard = "PRX_MECH_%s_GEN" % d["name"].upper()
+        w("// GENERATED by pelec_b200/mechgen/gen.py from pelec_b200/mechanisms/%s.json - do not edit." % d["name"])
+        w("// flavour: %s" % self.fl)
+        w("#ifndef %s" % guard)
+        w("#define %s" % guard)
+        if self.fl == "c":
+            w("#include <math.h>")
+        w("#ifndef PRX_RESTRICT")
+        w("#define PRX_RESTRICT %s" % ("__restrict__"))
+        w("#endif")
+        w("#define PRX_LN10 2.30258509299404568402")
+        w("#define PRX_MECH_NAME \"%s\"" % d["name"])
+        w("#define PRX_NUM_SPECIES %d" % N)
+        w("#define PRX_NUM_REACTIONS %d" % len(d["reactions"]))
+        w("#define PRX_RU %s" % d["Ru"])
+        w("#define PRX_TMIN %s" % lit(d["T_newton"]["tmin"]))
+        w("#define PRX_TMAX %s" % lit(d["T_newton"]["tmax"]))
+        w("#ifndef PRX_J")
+        w("#define PRX_J(row, col) J[(col) * %d + (row)]" % (N + 1))
+        w("#endif")
+        cq = "__device__ static const" if self.fl == "cuda" else "static const"
+        w("%s double prx_mw[%d] = {%s};" % (cq, N, ", ".join(d["mw"])))
+        w("%s double prx_imw[%d] = {%s};" % (cq, N, ", ".join(d["imw"])))
+        if self.fl == "c":
+            w("static const char* const prx_species_names[%d] = {%s};" % (N, ", ".join('"%s"' % s for s in d["species"])))
+        w()
+        self.emit_species_fn("cv_R", "cv_R", {"T2", "T3", "T4"})
+        self.emit_species_fn("cp_R", "cp_R", {"T2", "T3", "T4"})
+        self.emit_species_fn("gibbs", "gibbs", {"T2", "T3", "T4", "invT", "logT"})
+        self.emit_species_fn("e_RT_fn", "speciesInternalEnergy", {"T2", "T3", "T4", "invT"})
+        self.emit_species_fn("h_RT_fn", "speciesEnthalpy", {"T2", "T3", "T4", "invT"})
+        self.emit_species_fn("dcvpRdT", "dcvpRdT", {"T2", "T3"})
+        self.emit_mix_fn("ckcvbs", "cv_R", {"T2", "T3", "T4"}, False)
+        self.emit_mix_fn("ckcpbs", "cp_R", {"T2", "T3", "T4"}, False)
+        self.emit_mix_fn("ckubms", "speciesInternalEnergy", {"T2", "T3", "T4", "invT"}, True)
+        self.emit_mix_fn("ckhbms", "speciesEnthalpy", {"T2", "T3", "T4", "invT"}, True)
+        self.emit_production_rate()
+        self.emit_ajacobian()
+        w("#endif")
+        return "\n".join(self.L) + "\n"
+
+
+def emit(mech, flavour):
+    return Emitter(load(mech), flavour).emit()
+
+
+def write_if_changed(path, text):
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    if os.path.exists(path) and open(path).read() == text:
+        return False
+    with open(path, "w") as f:
+        f.write(text)
+    return True
+
+
+def generate_all(repo_root, mechs=("LiDryer", "drm19", "dodecane_lu")):
+    out = []
+    for m in mechs:
+        p = os.path.join(repo_root, "oracle", "gen", "mech_%s.h" % m)
+        write_if_changed(p, emit(m, "c"))
+        out.append(p)
+        p = os.path.join(repo_root, "pelec_b200", "csrc", "gen", "mech_%s.cuh" % m)
+        write_if_changed(p, emit(m, "cuda"))
+        out.append(p)
+    return out
+
+
+if __name__ == "__main__":
+    import sys
+    root = os.path.abspath(os.path.join(HERE, "..", ".."))
+    for p in generate_all(root, tuple(sys.argv[1:]) or ("LiDryer", "drm19", "dodecane_lu")):
+        print(os.path.relpath(p, root), os.path.getsize(p), "bytes")
