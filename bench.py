@@ -1,0 +1,379 @@
+#!/usr/bin/env python3
+"""bench.py - reacted cells/second of the chemistry hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--mech LiDryer|drm19|dodecane_lu] [--n 128] [--reactor ReactorCvode|ReactorRK64]
+
+One "step" = one ReactorBase::react call over one box of synthetic thermochemical states
+(ReactEval's initialize_data, PP/Testing/Exec/ReactEval/GPU_misc.H:13-82).  Default workload =
+BASELINE.json configs[1]: 128^3 LiDryer (H2/air) cells, ReactorCvode dense BDF with analytic Jacobian,
+dt = 1e-6 s, ReactEval tolerances (rtol = atol = 1e-10, cvode.max_order = 4; inputs.3d_Array4).
+
+N > 1 (torchrun, one rank per GPU): the path shards by box with no data-path collective - every rank
+reacts its own 128^3 box (weak scaling); one NCCL all-reduce sums the work counters at the end.
+
+`--impl reference` times the reference's own CPU reactor (oracle/_ref/libpeleref_<mech>.so, the unmodified
+PelePhysics ReactorCvode + SUNDIALS CVODE built by oracle/ref/Makefile; the oracle port if that library is
+absent) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "reacted_cells_per_sec"
+UNIT = "cells/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mech", default="LiDryer")
+    ap.add_argument("--n", type=int, default=128, help="box is n^3 cells")
+    ap.add_argument("--reactor", default="ReactorCvode", choices=["ReactorCvode", "ReactorRK64"])
+    ap.add_argument("--rtol", type=float, default=1e-10)
+    ap.add_argument("--atol", type=float, default=1e-10)
+    ap.add_argument("--max-order", type=int, default=4)
+    ap.add_argument("--dt", type=float, default=1e-6)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    tol = "rtol=%g atol=%g max_order=%d denseAJ_direct" % (a.rtol, a.atol, a.max_order)
+    if a.reactor == "ReactorRK64":
+        tol = "atol=%g" % a.atol
+    return "%d^3 synthetic %s states (ReactEval initialize_data), %s, dt=%g s, %s" % (
+        a.n, a.mech, a.reactor, a.dt, tol)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (reference / oracle port)
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """One process = one host core: react `ncells_j` j-lines of the workload with the CPU implementation."""
+    kind, mech, reactor, n, j_lo, j_hi, reps, rtol, atol, max_order, dt = args
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)  # the reference prints banners on stdout
+    from oracle.pyoracle import Oracle, Reference, reacteval_states
+    lib = Reference(mech) if kind == "reference" else Oracle(mech)
+    full = reacteval_states(lib, (1, n, 1))  # one cell per j: the states depend on j only
+    import numpy as np
+    idx = np.arange(j_lo, j_hi)
+    t0 = time.perf_counter()
+    cells = 0
+    for _ in range(reps):
+        s = full.take(idx)
+        if reactor == "ReactorCvode":
+            lib.react_cvode(s, dt, rtol=rtol, atol=atol, max_order=max_order, solve_type="denseAJ_direct")
+        else:
+            lib.react_rk64(s, dt, atol=atol)
+        cells += len(idx)
+    return cells, time.perf_counter() - t0
+
+
+def cpu_throughput(a, seconds):
+    """cells/s of the CPU implementation using every host core (one single-threaded process per core,
+    disjoint j-ranges: the path has no communication, so this equals an MPI run of the reference)."""
+    import multiprocessing as mp
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libpeleref_%s.so" % a.mech))
+    kind = "reference" if have_ref else "port"
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    n = a.n
+    # calibrate on one j-sweep in one process
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(1) as p:
+        c0, t0 = p.map(_cpu_worker, [(kind, a.mech, a.reactor, n, 0, n, 1, a.rtol, a.atol, a.max_order, a.dt)])[0]
+    per_sweep = max(t0, 1e-6)
+    reps = max(1, int(seconds / per_sweep))
+    jobs = [(kind, a.mech, a.reactor, n, 0, n, reps, a.rtol, a.atol, a.max_order, a.dt) for _ in range(cores)]
+    t_start = time.perf_counter()
+    with ctx.Pool(cores) as p:
+        res = p.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t_start
+    cells = sum(r[0] for r in res)
+    tmax = max(r[1] for r in res)
+    return {
+        "value": cells / tmax, "unit": UNIT, "cores": cores, "kind": kind,
+        "sample": "%d processes x %d sweeps of the %d distinct cell states of the workload (states depend on j only) "
+                  "= %d cell integrations in %.1f s" % (cores, reps, n, cells, wall),
+        "per_core": cells / tmax / cores,
+    }
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_throughput(a, max(20.0, a.cpu_seconds) / 1.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": None, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a)},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU leg
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.check_output(
+                    ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                    timeout=5).decode().strip()
+                self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        import statistics
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for i, nme in enumerate(names):
+                if len(s) > 3 + i and s[3 + i].lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def run_b200(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pelec_b200.mechgen import gen
+    from pelec_b200.reactor import Array4, Box, ReactorB200, load_library
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- synthetic states, built on the host by the generator's own EOS tables (no oracle involved):
+    # ReactEval's initialize_data needs X->Y and (P,Y,T)->(rho,e); compute them with the mechanism JSON.
+    N, n = gen.op_counts(a.mech)["N"], a.n
+    rY_h, T_h, rE_h = synth_states(a.mech, n)
+    ncell = n ** 3
+
+    def fab(t, ncomp):
+        return t.reshape(ncomp, n, n, n)
+    nbuf = a.steps + a.warmup
+    pristine = {
+        "rY": torch.from_numpy(rY_h).to(dev), "T": torch.from_numpy(T_h).to(dev), "rE": torch.from_numpy(rE_h).to(dev)}
+    rYsrc = torch.zeros((N, n, n, n), dtype=torch.float64, device=dev)
+    rEsrc = torch.zeros((1, n, n, n), dtype=torch.float64, device=dev)
+    mask = torch.ones((1, n, n, n), dtype=torch.int32, device=dev)
+    bufs = []
+    for _ in range(nbuf):  # one fresh copy of the in/out state per step: 128^3 x (N+3) doubles >> L2
+        bufs.append({"rY": fab(pristine["rY"].clone(), N), "T": fab(pristine["T"].clone(), 1),
+                     "rE": fab(pristine["rE"].clone(), 1),
+                     "FC": torch.zeros((1, n, n, n), dtype=torch.float64, device=dev)})
+
+    parm = {"ode__atol": a.atol}
+    if a.reactor == "ReactorCvode":
+        parm.update({"ode__rtol": a.rtol, "cvode__max_order": a.max_order, "cvode__solve_type": "denseAJ_direct"})
+    r = ReactorB200.create(a.reactor, a.mech, **parm)
+    r.init(1, 1, device=local)
+    box = Box((0, 0, 0), (n - 1, n - 1, n - 1))
+    stream = torch.cuda.current_stream(dev)
+
+    def step(b):
+        r.react(box, Array4(b["rY"]), Array4(rYsrc), Array4(b["T"]), Array4(b["rE"]), Array4(rEsrc), Array4(b["FC"]),
+                Array4(mask), a.dt, 0.0, stream=stream.cuda_stream)
+
+    for i in range(a.warmup):
+        step(bufs[i])
+    torch.cuda.synchronize(dev)
+    r.reset_stats()
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_all0.record(stream)
+    for i in range(a.steps):
+        ev[i][0].record(stream)
+        step(bufs[a.warmup + i])
+        ev[i][1].record(stream)
+    e_all1.record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag = True
+    total_ms = e_all0.elapsed_time(e_all1)
+    kern_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
+    stats = r.stats()
+
+    # ---- end-to-end through the host-buffer C-ABI call (pinned host memory, H2D + react + D2H per step)
+    hp = {k: torch.from_numpy(v).pin_memory() for k, v in (("rY", rY_h), ("T", T_h), ("rE", rE_h))}
+    h_rYsrc = torch.zeros(N * ncell, dtype=torch.float64).pin_memory()
+    h_rEsrc = torch.zeros(ncell, dtype=torch.float64).pin_memory()
+    h_FC = torch.zeros(ncell, dtype=torch.float64).pin_memory()
+    h_mask = torch.ones(ncell, dtype=torch.int32).pin_memory()
+    work = {k: v.clone().pin_memory() for k, v in hp.items()}
+    e2e_steps = max(1, min(a.steps, 3))
+    r.react_host(n, n, n, work["rY"], h_rYsrc, work["T"], work["rE"], h_rEsrc, h_FC, h_mask, a.dt, 0.0)  # warm-up
+    t_e2e = 0.0
+    for _ in range(e2e_steps):
+        for k in work:
+            work[k].copy_(hp[k])
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        r.react_host(n, n, n, work["rY"], h_rYsrc, work["T"], work["rE"], h_rEsrc, h_FC, h_mask, a.dt, 0.0)
+        t_e2e += time.perf_counter() - t0
+    h2d = (2 * N + 3) * 8 * ncell + 4 * ncell
+    d2h = (N + 3) * 8 * ncell
+
+    # ---- reductions over ranks: max time, summed counters (the only collective of the path)
+    t = torch.tensor([total_ms, t_e2e], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([stats[k] for k in ("cells", "n_steps", "n_rhs", "n_jac", "n_setups", "n_newton", "n_errfail",
+                                           "n_convfail", "n_failed")], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    total_ms, t_e2e = float(t[0]), float(t[1])
+    cells_all = ncell * a.steps * world
+    value = cells_all / (total_ms * 1e-3)
+    e2e_value = ncell * e2e_steps * world / t_e2e
+
+    if rank == 0:
+        oc = gen.op_counts(a.mech)
+        c = dict(zip(("cells", "n_steps", "n_rhs", "n_jac", "n_setups", "n_newton", "n_errfail", "n_convfail",
+                      "n_failed"), [float(x) for x in cnt]))
+        if a.reactor == "ReactorCvode":
+            flops = (c["n_rhs"] * (oc["F_rhs"] + oc["T_rhs"]) + c["n_jac"] * (oc["F_jac"] + oc["T_jac"])
+                     + c["n_setups"] * oc["F_lu"] + c["n_newton"] * oc["F_slv"] + c["n_steps"] * oc["F_vec"])
+        else:
+            flops = c["n_rhs"] * (oc["F_rhs"] + oc["T_rhs"]) + c["n_steps"] * oc["F_rk_update"]
+        flops_per_launch = flops / a.steps / world
+        kms = sum(kern_ms) / len(kern_ms)
+        lib = load_library()
+        peak = C.c_double(0.0)
+        lib.prx_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+        lib.prx_measure_fp64_peak(local, C.byref(peak))
+        achieved = flops_per_launch / (kms * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_alg = oc["bytes_per_cell"] * ncell / (kms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "mechanism": a.mech, "reactor": a.reactor,
+                       "cells_per_gpu_per_step": ncell, "sharding": "one %d^3 box per GPU, no data-path collective" % n,
+                       "l2": "each step reads/writes a fresh %.0f MB copy of the state (> 126 MB L2)"
+                             % ((2 * N + 6) * 8 * ncell / 1e6)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "prx_react_box_host (C ABI, pinned host buffers)"},
+            "gpu_launches": a.steps,
+            "roofline": {
+                "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
+                "frac": achieved / peak.value if peak.value > 0 else None, "traffic": None,
+                "peak_source": "measured in this run: register-resident DFMA chains (prx_measure_fp64_peak)",
+                "kernel": "bdf_kernel_%s" % a.mech if a.reactor == "ReactorCvode" else "rk64_kernel_%s" % a.mech,
+                "kernel_ms": kms, "flops_per_launch": flops_per_launch,
+                "flop_model": {k: oc[k] for k in ("F_rhs", "T_rhs", "F_jac", "T_jac", "F_lu", "F_slv", "F_vec")},
+                "hbm": {"algorithmic_GBps": hbm_alg, "peak_GBps": hbm_peak, "frac": hbm_alg / hbm_peak,
+                        "bytes_per_cell": oc["bytes_per_cell"], "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+            },
+            "counters_per_cell": {k: c[k] / max(c["cells"], 1) for k in ("n_steps", "n_rhs", "n_jac", "n_setups", "n_newton")},
+            "failed_cells": c["n_failed"],
+            "clocks": sampler.summary(),
+        }
+        if not a.no_cpu_baseline:
+            cb = cpu_throughput(a, a.cpu_seconds)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def synth_states(mech, n):
+    """ReactEval initialize_data (GPU_misc.H:13-82) for an n^3 box on [-1,1]^3, built on the host from the
+    mechanism table: X(fuel)=0.1, X(O2)=0.2, X(N2)=0.7, P=1 atm, T(y)=2000+500*y/L+100*sin(2*pi*y/(L/4)).
+    Returns SoA arrays rY[N*n^3], T[n^3], rE[n^3] (i fastest, then j, then k)."""
+    import numpy as np
+    from pelec_b200.mechgen import gen
+    d = gen.load(mech)
+    names = d["species"]
+    N = len(names)
+    mw = np.array([float(x) for x in d["mw"]])
+    imw = np.array([float(x) for x in d["imw"]])
+    Ru = float(d["Ru"])
+    fuel = {"LiDryer": "H2", "drm19": "CH4", "dodecane_lu": "NC12H26"}[mech]
+    X = np.zeros(N)
+    X[names.index("O2")], X[names.index(fuel)], X[names.index("N2")] = 0.2, 0.1, 0.7
+    Y = X * mw / (X * mw).sum()
+    y = -1.0 + (np.arange(n) + 0.5) * (2.0 / n)
+    Tj = 2000.0 + 500.0 * y / 2.0 + 100.0 * np.sin(2.0 * 3.1415926535897932 * y / 0.5)
+    rho = 1013250.0 / (Ru * Tj * (Y * imw).sum())
+    # species internal energies e_k(T)/RT from the NASA-7 table (speciesInternalEnergy literals)
+    th = d["thermo"]["speciesInternalEnergy"]
+    basis = {"1": lambda T: np.ones_like(T), "T": lambda T: T, "T2": lambda T: T * T, "T3": lambda T: T ** 3,
+             "T4": lambda T: T ** 4, "invT": lambda T: 1.0 / T}
+    e = np.zeros(n)
+    for k in range(N):
+        if Y[k] == 0.0:
+            continue
+        tm = th[k]["tmid"]
+        lo = sum(float(c) * basis[b](Tj) for c, b in th[k]["lo"])
+        hi = sum(float(c) * basis[b](Tj) for c, b in th[k]["hi"])
+        ek = np.where(Tj < (tm if tm is not None else 1e99), lo, hi)
+        e += Y[k] * ek * Ru * Tj * imw[k]
+    jj = np.tile(np.repeat(np.arange(n), n), n)
+    rY = (Y[:, None] * rho[jj][None, :]).reshape(-1).copy()
+    return rY, Tj[jj].copy(), (rho * e)[jj].copy()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,187 @@
+/* pelerx_b200.h - C ABI of the B200-native (sm_100a) stiff-chemistry reactor.
+ *
+ * This is the drop-in boundary for ONE hot path of PeleC / PelePhysics: the pointwise
+ * chemistry advance behind pele::physics::reactions::ReactorBase
+ * (PP/Source/Reactions/ReactorBase.H:14-106), i.e. what PeleC::react_state
+ * (PC/Source/React.cpp:222-228) and ReactEval (PP/Testing/Exec/ReactEval/main.cpp:516-522)
+ * call once per AMReX box.  A thin C++ shim (integration/ReactorB200.{H,cpp}) derives from
+ * ReactorBase::Register<> and only unpacks amrex::Box / amrex::Array4 into the PODs below.
+ *
+ * Conventions
+ *   - every entry point returns 0 on success, a negative prx_status otherwise; nothing
+ *     aborts (the reference calls amrex::Abort, PP/Source/Reactions/ReactorUtils.cpp:12-46);
+ *   - all array pointers are DEVICE pointers unless the function name ends in _host;
+ *   - calls are asynchronous on the given CUDA stream (the caller synchronises, as
+ *     PC/Source/React.cpp:230 does) except prx_get_stats / *_host which synchronise;
+ *   - there is NO CPU fallback: without a CUDA device prx_create fails with PRX_ERR_NO_DEVICE.
+ *
+ * (PC = /root/reference, PP = PC/Submodules/PelePhysics.)
+ */
+#ifndef PELERX_B200_H
+#define PELERX_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRX_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PRX_API __attribute__((visibility("default")))
+#else
+#define PRX_API
+#endif
+
+typedef enum {
+  PRX_OK = 0,
+  PRX_ERR_BAD_ARG = -1,      /* null pointer, bad size, unknown enum value */
+  PRX_ERR_NO_DEVICE = -2,    /* no CUDA device / driver: the library never computes on the CPU */
+  PRX_ERR_CUDA = -3,         /* a CUDA runtime call failed; see prx_last_error */
+  PRX_ERR_UNSUPPORTED = -4,  /* option the reference has but this path does not implement */
+  PRX_ERR_ALLOC = -5
+} prx_status;
+
+/* compile-time mechanisms (the reference selects one per executable through
+ * Chemistry_Model / NUM_SPECIES, PC/Exec/Make.PeleC:75-81; here all are linked in) */
+typedef enum {
+  PRX_MECH_LIDRYER = 0,      /* PP/Mechanisms/LiDryer      9 species, 21 reactions  */
+  PRX_MECH_DRM19 = 1,        /* PP/Mechanisms/drm19       21 species, 84 reactions  */
+  PRX_MECH_DODECANE_LU = 2   /* PP/Mechanisms/dodecane_lu 53 species, 268 reactions */
+} prx_mechanism;
+
+/* pelec.chem_integrator / chem_integrator keys (PC/Source/Params/_cpp_parameters:302-305) */
+typedef enum {
+  PRX_REACTOR_RK64 = 0,      /* "ReactorRK64"  PP/Source/Reactions/ReactorRK64.cpp:166-320  */
+  PRX_REACTOR_CVODE = 1      /* "ReactorCvode" PP/Source/Reactions/ReactorCvode.cpp:1267-1489,
+                                per-cell (CPU-branch) semantics: one BDF integration per cell */
+} prx_reactor_kind;
+
+/* cvode.solve_type (PP/Source/Reactions/ReactorCvode.cpp:507-934) */
+typedef enum {
+  PRX_SOLVE_DENSE_AJ_DIRECT = 0, /* "denseAJ_direct": analytic Jacobian + dense LU   */
+  PRX_SOLVE_DENSE_DIRECT = 1     /* "dense_direct":   difference-quotient J + dense LU */
+} prx_solve_type;
+
+/* Filled by the shim from the same ParmParse keys the reference reads
+ * (ode.* / cvode.*: ReactorCvode.cpp:18-35, ReactorRK64.cpp:12-18). */
+typedef struct prx_config {
+  int abi_version;          /* PRX_ABI_VERSION */
+  int mechanism;            /* prx_mechanism */
+  int reactor_kind;         /* prx_reactor_kind */
+  int reactor_type;         /* 1 = e (UV, PeleC), 2 = h (HP, PeleLM): ReactorTypes.H:8-20 */
+  double rtol;              /* ode.rtol  (CVODE only) */
+  double atol;              /* ode.atol  */
+  int max_order;            /* cvode.max_order (default 2, ReactorCvode.H:191) */
+  int max_nls_iters;        /* ode.max_nls_iters (default 3) */
+  int solve_type;           /* prx_solve_type */
+  int rk64_nsubsteps_guess; /* ode.rk64_nsubsteps_guess (10)  */
+  int rk64_nsubsteps_min;   /* ode.rk64_nsubsteps_min   (5)   */
+  int rk64_nsubsteps_max;   /* ode.rk64_nsubsteps_max   (500) */
+  int clean_init_massfrac;  /* ode.clean_init_massfrac (0) */
+  int verbose;              /* ode.verbose */
+  int device;               /* CUDA device ordinal, -1 = current device */
+} prx_config;
+
+/* Same fields and meaning as amrex::Array4<T> (AMR/Src/Base/AMReX_Array4.H:60-68):
+ * element (i,j,k,n) is p[(i-begin[0]) + (j-begin[1])*jstride + (k-begin[2])*kstride + n*nstride]. */
+typedef struct prx_array4 {
+  double* p;
+  long long jstride, kstride, nstride;
+  int begin[3];
+  int end[3]; /* exclusive, as in AMReX */
+  int ncomp;
+} prx_array4;
+
+typedef struct prx_array4i {
+  int* p;
+  long long jstride, kstride, nstride;
+  int begin[3];
+  int end[3];
+  int ncomp;
+} prx_array4i;
+
+/* Work counters accumulated on the device since the last prx_reset_stats: the analogue of
+ * CVODE's final statistics (ReactorCvode.cpp:1838-1901) and the input of the FLOP model
+ * (SURVEY.md 8d).  Plain sums over cells so that ranks can be combined with one all-reduce. */
+typedef struct prx_stats {
+  long long cells;          /* cells integrated                                   */
+  long long cells_masked;   /* cells skipped because mask == -1                   */
+  long long n_steps;        /* internal steps (RK64 steps | CVODE nst)            */
+  long long n_rhs;          /* RHS evaluations (RK64: 6/step | CVODE nfe + nfeDQ) */
+  long long n_jac;          /* Jacobian evaluations (nje)                         */
+  long long n_setups;       /* LU factorisations (nsetups)                        */
+  long long n_newton;       /* Newton iterations = linear solves (nni)            */
+  long long n_errfail;      /* error-test failures (netf)                         */
+  long long n_convfail;     /* nonlinear convergence failures (ncfn)              */
+  long long n_failed;       /* cells whose integrator returned a failure flag     */
+  long long max_steps;      /* max internal steps over cells                      */
+  long long reserved;
+} prx_stats;
+
+typedef struct prx_handle prx_handle;
+
+/* ---- life cycle: ReactorBase::create + init / close (ReactorBase.H:20-23) ---- */
+PRX_API int prx_create(const prx_config* cfg, prx_handle** out);
+PRX_API int prx_destroy(prx_handle* h);
+/* ReactorBase::set_typ_vals_ode (ReactorBase.cpp:6-31): n must be NUM_SPECIES+1 */
+PRX_API int prx_set_typ_vals(prx_handle* h, const double* typ_vals_host, int n);
+PRX_API const char* prx_last_error(const prx_handle* h);
+PRX_API int prx_num_species(int mechanism);
+PRX_API int prx_num_reactions(int mechanism);
+PRX_API const char* prx_mechanism_name(int mechanism);
+PRX_API int prx_default_config(prx_config* cfg);
+
+/* ---- ReactorBase::react, Array4 version (ReactorBase.H:25-40) ----
+ * box = [lo, hi] inclusive.  rY in/out [N], rYsrc in [N], T in/out, rE in/out (+= dt*rEsrc),
+ * rEsrc in, FC out (work count as double), mask in (-1 = skip; honoured by the CVODE reactor,
+ * ignored by RK64, as in the reference).  Returns 0; the reference's return value (average
+ * RK64 steps per cell / dummy 20) is available as prx_last_react_return(). */
+PRX_API int prx_react_box(
+  prx_handle* h, const int lo[3], const int hi[3], const prx_array4* rY, const prx_array4* rYsrc,
+  const prx_array4* T, const prx_array4* rE, const prx_array4* rEsrc, const prx_array4* FC,
+  const prx_array4i* mask, double dt, double time, void* cuda_stream);
+
+/* ---- ReactorBase::react, flat version (ReactorBase.H:42-54), DEVICE pointers ----
+ * y [ncells*(N+1)] YCOrder (cell-major, T last), ysrc [ncells*N], e [ncells], esrc [ncells].
+ * Reference semantics of the 1-D call: T is taken from y (no initial REY2T) and the
+ * integrated T is returned (ReactorRK64.cpp:82-96,140-143). fc may be NULL. */
+PRX_API int prx_react_flat(
+  prx_handle* h, double* y, const double* ysrc, double* e, const double* esrc, double* fc,
+  double dt, double time, int ncells, void* cuda_stream);
+
+/* ---- ReactorBase::flatten / unflatten (ReactorBase.H:56-80; ReactorUtils.H:301-355) ---- */
+PRX_API int prx_flatten(
+  prx_handle* h, const int lo[3], const int hi[3], const prx_array4* rY, const prx_array4* rYsrc,
+  const prx_array4* T, const prx_array4* rE, const prx_array4* rEsrc, double* y, double* ysrc,
+  double* e, double* esrc, void* cuda_stream);
+PRX_API int prx_unflatten(
+  prx_handle* h, const int lo[3], const int hi[3], const prx_array4* rY, const prx_array4* T,
+  const prx_array4* rE, const prx_array4* rEsrc, const prx_array4* FC, const double* y,
+  const double* e, const double* fc, double dt, void* cuda_stream);
+
+/* ---- host-buffer convenience: one box held as SoA host arrays a[comp*ncells + cell]
+ * (component stride = ncells, exactly an AMReX FAB); does H2D, react, D2H and synchronises.
+ * This is the call the end-to-end benchmark and the ctypes tests use. */
+PRX_API int prx_react_box_host(
+  prx_handle* h, int nx, int ny, int nz, double* rY, const double* rYsrc, double* T, double* rE,
+  const double* rEsrc, double* FC, const int* mask, double dt, double time);
+
+/* ---- statistics ---- */
+PRX_API int prx_reset_stats(prx_handle* h);
+PRX_API int prx_get_stats(prx_handle* h, prx_stats* out); /* synchronises the handle's streams */
+PRX_API int prx_last_react_return(prx_handle* h);        /* value ReactorBase::react would return */
+
+/* ---- device probes used by the parity tests (n states, state-major host arrays) ---- */
+PRX_API int prx_probe_rhs_host(
+  prx_handle* h, int n, double t, const double* y, const double* rhoe_init, const double* rhoesrc,
+  const double* rYsrc, double* ydot);
+PRX_API int prx_probe_jac_host(prx_handle* h, int n, const double* y, double* J /* [n][(N+1)^2] col-major */);
+
+/* ---- measurement helper: sustained FP64 FMA rate of the device [TFLOP/s] (register-resident DFMA
+ * chains), the denominator of the FP64 roofline that bench.py reports ---- */
+PRX_API int prx_measure_fp64_peak(int device, double* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

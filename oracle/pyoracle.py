@@ -115,9 +115,10 @@ class Oracle:
         return rho, e
 
     def x2y(self, X):
-        X = np.atleast_2d(X)
-        Y = X * self.mw[None, :]
-        return Y / Y.sum(axis=1, keepdims=True)
+        X = np.ascontiguousarray(np.atleast_2d(X), dtype=float)
+        Y = np.zeros_like(X)
+        self.lib.orc_x2y(X.shape[0], _p(X), _p(Y))
+        return Y
 
     def ey2t(self, e, Y, Tguess):
         T = np.array(Tguess, dtype=float).copy()

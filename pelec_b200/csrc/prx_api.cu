@@ -1,0 +1,649 @@
+// prx_api.cu - the C ABI of include/pelerx_b200.h: handle life cycle, argument checking,
+// Array4 -> kernel views, per-mechanism dispatch, statistics.  No chemistry in this file and no
+// CPU compute path: if there is no CUDA device, prx_create fails.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "prx_kernels.cuh"
+
+using namespace prx;
+
+struct prx_handle
+{
+  prx_config cfg;
+  const MechOps* ops;
+  int device;
+  std::vector<double> typ_vals; // size N+1; typ_vals[0] <= 0: not set
+  DevStats* d_stats;
+  int* d_queues; // ring of work-queue counters: one per in-flight launch
+  int n_queues;
+  int q_next;
+  SchedParams sched;
+  long long last_ncells;
+  // staging for the *_host convenience calls
+  double* d_stage;
+  size_t d_stage_bytes;
+  cudaStream_t stage_stream;
+  char err[512];
+};
+
+namespace {
+
+const MechOps* ops_for(int mech)
+{
+  switch (mech) {
+  case PRX_MECH_LIDRYER:
+    return mech_ops_LiDryer();
+  case PRX_MECH_DRM19:
+    return mech_ops_drm19();
+  case PRX_MECH_DODECANE_LU:
+    return mech_ops_dodecane_lu();
+  default:
+    return nullptr;
+  }
+}
+
+int fail(prx_handle* h, int code, const char* what, cudaError_t ce = cudaSuccess)
+{
+  if (h != nullptr) {
+    if (ce != cudaSuccess) {
+      std::snprintf(h->err, sizeof(h->err), "%s: %s", what, cudaGetErrorString(ce));
+    } else {
+      std::snprintf(h->err, sizeof(h->err), "%s", what);
+    }
+  }
+  return code;
+}
+
+#define PRX_CUDA(h, call)                            \
+  do {                                               \
+    const cudaError_t ce__ = (call);                 \
+    if (ce__ != cudaSuccess) {                       \
+      return fail((h), PRX_ERR_CUDA, #call, ce__);   \
+    }                                                \
+  } while (0)
+
+struct DeviceGuard
+{
+  int prev;
+  bool active;
+  explicit DeviceGuard(int dev) : prev(0), active(false)
+  {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+      active = (cudaSetDevice(dev) == cudaSuccess);
+    }
+  }
+  ~DeviceGuard()
+  {
+    if (active) {
+      cudaSetDevice(prev);
+    }
+  }
+};
+
+bool view_of(const prx_array4* a, const int lo[3], int need_comp, ArrView* v)
+{
+  if (a == nullptr || a->p == nullptr || a->ncomp < need_comp) {
+    return false;
+  }
+  for (int d = 0; d < 3; d++) {
+    if (lo[d] < a->begin[d]) {
+      return false;
+    }
+  }
+  v->js = a->jstride;
+  v->ks = a->kstride;
+  v->ns = a->nstride;
+  v->p = a->p + (lo[0] - a->begin[0]) + (long long)(lo[1] - a->begin[1]) * a->jstride +
+         (long long)(lo[2] - a->begin[2]) * a->kstride;
+  return true;
+}
+
+int* next_queue(prx_handle* h)
+{
+  int* q = h->d_queues + h->q_next;
+  h->q_next = (h->q_next + 1) % h->n_queues;
+  return q;
+}
+
+int ensure_stage(prx_handle* h, size_t bytes)
+{
+  if (bytes <= h->d_stage_bytes) {
+    return PRX_OK;
+  }
+  if (h->d_stage != nullptr) {
+    cudaFree(h->d_stage);
+    h->d_stage = nullptr;
+    h->d_stage_bytes = 0;
+  }
+  PRX_CUDA(h, cudaMalloc(&h->d_stage, bytes));
+  h->d_stage_bytes = bytes;
+  return PRX_OK;
+}
+
+int env_int(const char* name, int dflt)
+{
+  const char* s = std::getenv(name);
+  return (s != nullptr && *s) ? std::atoi(s) : dflt;
+}
+
+} // namespace
+
+// Register-resident DFMA chains: the measured FP64 roofline denominator (MEASURED_PEAKS.json has only
+// HBM and bf16).  8 independent accumulators per thread, 2 flops per FMA.
+__global__ void fp64_peak_kernel(double* out, const int iters, const double a, const double b)
+{
+  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+         x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+    x0 = fma(x0, a, b);
+    x1 = fma(x1, a, b);
+    x2 = fma(x2, a, b);
+    x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b);
+    x5 = fma(x5, a, b);
+    x6 = fma(x6, a, b);
+    x7 = fma(x7, a, b);
+  }
+  const double r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (r == 123.456) {
+    out[0] = r;
+  }
+}
+
+extern "C" {
+
+int prx_measure_fp64_peak(int device, double* tflops_out)
+{
+  if (tflops_out == nullptr) {
+    return PRX_ERR_BAD_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return PRX_ERR_NO_DEVICE;
+  }
+  if (device < 0) {
+    cudaGetDevice(&device);
+  }
+  DeviceGuard g(device);
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  double* d = nullptr;
+  if (cudaMalloc(&d, sizeof(double)) != cudaSuccess) {
+    return PRX_ERR_CUDA;
+  }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int threads = 256, blocks = sms * 8, iters = 1 << 15;
+  double best = 0.0;
+  for (int rep = 0; rep < 6; rep++) {
+    cudaEventRecord(e0);
+    fp64_peak_kernel<<<blocks, threads>>>(d, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) {
+      break;
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = 2.0 * 8.0 * (double)iters * threads * (double)blocks;
+    const double tf = fl / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) {
+      best = tf;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops_out = best;
+  return (cudaGetLastError() == cudaSuccess) ? PRX_OK : PRX_ERR_CUDA;
+}
+
+int prx_default_config(prx_config* cfg)
+{
+  if (cfg == nullptr) {
+    return PRX_ERR_BAD_ARG;
+  }
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->abi_version = PRX_ABI_VERSION;
+  cfg->mechanism = PRX_MECH_LIDRYER;
+  cfg->reactor_kind = PRX_REACTOR_CVODE;
+  cfg->reactor_type = 1;
+  cfg->rtol = 1e-6;  // ReactorCvode.H:179-191 defaults
+  cfg->atol = 1e-10;
+  cfg->max_order = 2;
+  cfg->max_nls_iters = 3;
+  cfg->solve_type = PRX_SOLVE_DENSE_AJ_DIRECT;
+  cfg->rk64_nsubsteps_guess = 10;
+  cfg->rk64_nsubsteps_min = 5;
+  cfg->rk64_nsubsteps_max = 500;
+  cfg->clean_init_massfrac = 0;
+  cfg->verbose = 0;
+  cfg->device = -1;
+  return PRX_OK;
+}
+
+int prx_num_species(int mechanism)
+{
+  const MechOps* o = ops_for(mechanism);
+  return o ? o->num_species : PRX_ERR_BAD_ARG;
+}
+int prx_num_reactions(int mechanism)
+{
+  const MechOps* o = ops_for(mechanism);
+  return o ? o->num_reactions : PRX_ERR_BAD_ARG;
+}
+const char* prx_mechanism_name(int mechanism)
+{
+  const MechOps* o = ops_for(mechanism);
+  return o ? o->name : nullptr;
+}
+
+int prx_create(const prx_config* cfg, prx_handle** out)
+{
+  if (cfg == nullptr || out == nullptr) {
+    return PRX_ERR_BAD_ARG;
+  }
+  *out = nullptr;
+  if (cfg->abi_version != PRX_ABI_VERSION) {
+    return PRX_ERR_BAD_ARG;
+  }
+  const MechOps* ops = ops_for(cfg->mechanism);
+  if (ops == nullptr) {
+    return PRX_ERR_BAD_ARG;
+  }
+  if (cfg->reactor_kind != PRX_REACTOR_RK64 && cfg->reactor_kind != PRX_REACTOR_CVODE) {
+    return PRX_ERR_BAD_ARG;
+  }
+  if (cfg->reactor_type != 1 && cfg->reactor_type != 2) {
+    return PRX_ERR_BAD_ARG; // reference: amrex::Abort("Wrong reactor type. Choose between 1 (e) or 2 (h).")
+  }
+  if (cfg->reactor_kind == PRX_REACTOR_CVODE) {
+    if (cfg->max_order < 1 || cfg->max_order > 5 || cfg->max_nls_iters < 1 || !(cfg->rtol > 0.0) || !(cfg->atol > 0.0)) {
+      return PRX_ERR_BAD_ARG;
+    }
+    if (cfg->solve_type != PRX_SOLVE_DENSE_AJ_DIRECT && cfg->solve_type != PRX_SOLVE_DENSE_DIRECT) {
+      return PRX_ERR_UNSUPPORTED;
+    }
+  } else {
+    if (cfg->rk64_nsubsteps_guess < 1 || cfg->rk64_nsubsteps_min < 1 || cfg->rk64_nsubsteps_max < 1 || !(cfg->atol > 0.0)) {
+      return PRX_ERR_BAD_ARG;
+    }
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return PRX_ERR_NO_DEVICE; // no CPU fallback, by design
+  }
+  int dev = cfg->device;
+  if (dev < 0) {
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+      return PRX_ERR_NO_DEVICE;
+    }
+  }
+  if (dev >= ndev) {
+    return PRX_ERR_BAD_ARG;
+  }
+  prx_handle* h = new (std::nothrow) prx_handle();
+  if (h == nullptr) {
+    return PRX_ERR_ALLOC;
+  }
+  h->cfg = *cfg;
+  h->ops = ops;
+  h->device = dev;
+  h->typ_vals.assign(ops->num_species + 1, -1.0);
+  h->d_stats = nullptr;
+  h->d_queues = nullptr;
+  h->n_queues = 256;
+  h->q_next = 0;
+  h->sched.jac_defer_min_lanes = env_int("PRX_JAC_DEFER", 1);
+  h->sched.lu_defer_min_lanes = env_int("PRX_LU_DEFER", 1);
+  h->last_ncells = 0;
+  h->d_stage = nullptr;
+  h->d_stage_bytes = 0;
+  h->stage_stream = nullptr;
+  h->err[0] = 0;
+  DeviceGuard g(dev);
+  if (cudaMalloc(&h->d_stats, sizeof(DevStats)) != cudaSuccess ||
+      cudaMalloc(&h->d_queues, sizeof(int) * h->n_queues) != cudaSuccess ||
+      cudaMemset(h->d_stats, 0, sizeof(DevStats)) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->stage_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    prx_destroy(h);
+    return PRX_ERR_CUDA;
+  }
+  *out = h;
+  return PRX_OK;
+}
+
+int prx_destroy(prx_handle* h)
+{
+  if (h == nullptr) {
+    return PRX_ERR_BAD_ARG;
+  }
+  DeviceGuard g(h->device);
+  cudaDeviceSynchronize();
+  if (h->d_stats) {
+    cudaFree(h->d_stats);
+  }
+  if (h->d_queues) {
+    cudaFree(h->d_queues);
+  }
+  if (h->d_stage) {
+    cudaFree(h->d_stage);
+  }
+  if (h->stage_stream) {
+    cudaStreamDestroy(h->stage_stream);
+  }
+  delete h;
+  return PRX_OK;
+}
+
+int prx_set_typ_vals(prx_handle* h, const double* typ, int n)
+{
+  if (h == nullptr || typ == nullptr) {
+    return PRX_ERR_BAD_ARG;
+  }
+  if (n != h->ops->num_species + 1) {
+    return fail(h, PRX_ERR_BAD_ARG, "prx_set_typ_vals: n must be NUM_SPECIES+1");
+  }
+  for (int k = 0; k < n; k++) {
+    h->typ_vals[k] = typ[k];
+  }
+  return PRX_OK;
+}
+
+const char* prx_last_error(const prx_handle* h) { return h ? h->err : "null handle"; }
+
+static int react_args(prx_handle* h, const BoxArgs& a, cudaStream_t stream)
+{
+  DeviceGuard g(h->device);
+  // per-launch step sum (for the value ReactorBase::react returns)
+  PRX_CUDA(h, cudaMemsetAsync(&h->d_stats->v[ST_LAST_STEPS], 0, sizeof(unsigned long long), stream));
+  h->last_ncells = a.ncells;
+  cudaError_t e;
+  if (h->cfg.reactor_kind == PRX_REACTOR_RK64) {
+    e = h->ops->launch_rk64(a, h->cfg, next_queue(h), h->d_stats, stream);
+  } else {
+    e = h->ops->launch_bdf(a, h->cfg, h->typ_vals.data(), next_queue(h), h->d_stats, h->sched, stream);
+  }
+  if (e != cudaSuccess) {
+    return fail(h, PRX_ERR_CUDA, "kernel launch", e);
+  }
+  return PRX_OK;
+}
+
+int prx_react_box(
+  prx_handle* h, const int lo[3], const int hi[3], const prx_array4* rY, const prx_array4* rYsrc,
+  const prx_array4* T, const prx_array4* rE, const prx_array4* rEsrc, const prx_array4* FC,
+  const prx_array4i* mask, double dt, double time, void* cuda_stream)
+{
+  if (h == nullptr || lo == nullptr || hi == nullptr) {
+    return PRX_ERR_BAD_ARG;
+  }
+  const int N = h->ops->num_species;
+  BoxArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.layout = LAYOUT_ARRAY4;
+  long long nc = 1;
+  for (int d = 0; d < 3; d++) {
+    a.len[d] = hi[d] - lo[d] + 1;
+    if (a.len[d] <= 0) {
+      a.len[d] = 0;
+    }
+    nc *= a.len[d];
+  }
+  if (nc == 0) {
+    return PRX_OK; // empty box: nothing to do (amrex::ParallelFor over an empty box)
+  }
+  if (nc > 2147483647LL) {
+    return fail(h, PRX_ERR_BAD_ARG, "box too large (int32 cell index)");
+  }
+  a.ncells = (int)nc;
+  if (!view_of(rY, lo, N, &a.rY) || !view_of(rYsrc, lo, N, &a.rYsrc) || !view_of(T, lo, 1, &a.T) ||
+      !view_of(rE, lo, 1, &a.rE) || !view_of(rEsrc, lo, 1, &a.rEsrc) || !view_of(FC, lo, 1, &a.FC)) {
+    return fail(h, PRX_ERR_BAD_ARG, "prx_react_box: null/short Array4 or box outside the array");
+  }
+  if (mask != nullptr && mask->p != nullptr) {
+    a.mask.js = mask->jstride;
+    a.mask.ks = mask->kstride;
+    a.mask.ns = mask->nstride;
+    a.mask.p = mask->p + (lo[0] - mask->begin[0]) + (long long)(lo[1] - mask->begin[1]) * mask->jstride +
+               (long long)(lo[2] - mask->begin[2]) * mask->kstride;
+  }
+  a.dt = dt;
+  a.time = time;
+  return react_args(h, a, (cudaStream_t)cuda_stream);
+}
+
+int prx_react_flat(
+  prx_handle* h, double* y, const double* ysrc, double* e, const double* esrc, double* fc, double dt,
+  double time, int ncells, void* cuda_stream)
+{
+  if (h == nullptr || ncells < 0) {
+    return PRX_ERR_BAD_ARG;
+  }
+  if (ncells == 0) {
+    return PRX_OK;
+  }
+  if (y == nullptr || ysrc == nullptr || e == nullptr || esrc == nullptr) {
+    return fail(h, PRX_ERR_BAD_ARG, "prx_react_flat: null pointer");
+  }
+  BoxArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.layout = LAYOUT_FLAT;
+  a.ncells = ncells;
+  a.len[0] = ncells;
+  a.len[1] = a.len[2] = 1;
+  a.y = y;
+  a.ysrc = ysrc;
+  a.e = e;
+  a.esrc = esrc;
+  a.fc = fc;
+  a.dt = dt;
+  a.time = time;
+  return react_args(h, a, (cudaStream_t)cuda_stream);
+}
+
+int prx_react_box_host(
+  prx_handle* h, int nx, int ny, int nz, double* rY, const double* rYsrc, double* T, double* rE,
+  const double* rEsrc, double* FC, const int* mask, double dt, double time)
+{
+  if (h == nullptr || nx < 0 || ny < 0 || nz < 0) {
+    return PRX_ERR_BAD_ARG;
+  }
+  const long long nc = (long long)nx * ny * nz;
+  if (nc == 0) {
+    return PRX_OK;
+  }
+  if (rY == nullptr || rYsrc == nullptr || T == nullptr || rE == nullptr || rEsrc == nullptr || FC == nullptr) {
+    return fail(h, PRX_ERR_BAD_ARG, "prx_react_box_host: null pointer");
+  }
+  DeviceGuard g(h->device);
+  const int N = h->ops->num_species;
+  // device staging: [rY N][rYsrc N][T][rE][rEsrc][FC] doubles + mask ints
+  const size_t nd = (size_t)(2 * N + 4) * nc;
+  const size_t bytes = nd * sizeof(double) + (size_t)nc * sizeof(int);
+  const int rc = ensure_stage(h, bytes);
+  if (rc != PRX_OK) {
+    return rc;
+  }
+  cudaStream_t st = h->stage_stream;
+  double* d_rY = h->d_stage;
+  double* d_rYsrc = d_rY + (size_t)N * nc;
+  double* d_T = d_rYsrc + (size_t)N * nc;
+  double* d_rE = d_T + nc;
+  double* d_rEsrc = d_rE + nc;
+  double* d_FC = d_rEsrc + nc;
+  int* d_mask = reinterpret_cast<int*>(d_FC + nc);
+  PRX_CUDA(h, cudaMemcpyAsync(d_rY, rY, sizeof(double) * N * nc, cudaMemcpyHostToDevice, st));
+  PRX_CUDA(h, cudaMemcpyAsync(d_rYsrc, rYsrc, sizeof(double) * N * nc, cudaMemcpyHostToDevice, st));
+  PRX_CUDA(h, cudaMemcpyAsync(d_T, T, sizeof(double) * nc, cudaMemcpyHostToDevice, st));
+  PRX_CUDA(h, cudaMemcpyAsync(d_rE, rE, sizeof(double) * nc, cudaMemcpyHostToDevice, st));
+  PRX_CUDA(h, cudaMemcpyAsync(d_rEsrc, rEsrc, sizeof(double) * nc, cudaMemcpyHostToDevice, st));
+  if (mask != nullptr) {
+    PRX_CUDA(h, cudaMemcpyAsync(d_mask, mask, sizeof(int) * nc, cudaMemcpyHostToDevice, st));
+  }
+  const int lo[3] = {0, 0, 0};
+  const int hi[3] = {nx - 1, ny - 1, nz - 1};
+  auto mk = [&](double* p, int ncomp) {
+    prx_array4 a;
+    a.p = p;
+    a.jstride = nx;
+    a.kstride = (long long)nx * ny;
+    a.nstride = nc;
+    a.begin[0] = a.begin[1] = a.begin[2] = 0;
+    a.end[0] = nx;
+    a.end[1] = ny;
+    a.end[2] = nz;
+    a.ncomp = ncomp;
+    return a;
+  };
+  prx_array4 a_rY = mk(d_rY, N), a_rYsrc = mk(d_rYsrc, N), a_T = mk(d_T, 1), a_rE = mk(d_rE, 1),
+             a_rEsrc = mk(d_rEsrc, 1), a_FC = mk(d_FC, 1);
+  prx_array4i a_mask;
+  a_mask.p = (mask != nullptr) ? d_mask : nullptr;
+  a_mask.jstride = nx;
+  a_mask.kstride = (long long)nx * ny;
+  a_mask.nstride = nc;
+  a_mask.begin[0] = a_mask.begin[1] = a_mask.begin[2] = 0;
+  a_mask.end[0] = nx;
+  a_mask.end[1] = ny;
+  a_mask.end[2] = nz;
+  a_mask.ncomp = 1;
+  const int r = prx_react_box(h, lo, hi, &a_rY, &a_rYsrc, &a_T, &a_rE, &a_rEsrc, &a_FC, &a_mask, dt, time, st);
+  if (r != PRX_OK) {
+    return r;
+  }
+  PRX_CUDA(h, cudaMemcpyAsync(rY, d_rY, sizeof(double) * N * nc, cudaMemcpyDeviceToHost, st));
+  PRX_CUDA(h, cudaMemcpyAsync(T, d_T, sizeof(double) * nc, cudaMemcpyDeviceToHost, st));
+  PRX_CUDA(h, cudaMemcpyAsync(rE, d_rE, sizeof(double) * nc, cudaMemcpyDeviceToHost, st));
+  PRX_CUDA(h, cudaMemcpyAsync(FC, d_FC, sizeof(double) * nc, cudaMemcpyDeviceToHost, st));
+  PRX_CUDA(h, cudaStreamSynchronize(st));
+  return PRX_OK;
+}
+
+int prx_flatten(
+  prx_handle* h, const int*, const int*, const prx_array4*, const prx_array4*, const prx_array4*,
+  const prx_array4*, const prx_array4*, double*, double*, double*, double*, void*)
+{
+  return fail(h, PRX_ERR_UNSUPPORTED, "prx_flatten: not implemented yet (flatten is fused into the react kernels)");
+}
+int prx_unflatten(
+  prx_handle* h, const int*, const int*, const prx_array4*, const prx_array4*, const prx_array4*,
+  const prx_array4*, const prx_array4*, const double*, const double*, const double*, double, void*)
+{
+  return fail(h, PRX_ERR_UNSUPPORTED, "prx_unflatten: not implemented yet (unflatten is fused into the react kernels)");
+}
+
+int prx_reset_stats(prx_handle* h)
+{
+  if (h == nullptr) {
+    return PRX_ERR_BAD_ARG;
+  }
+  DeviceGuard g(h->device);
+  PRX_CUDA(h, cudaDeviceSynchronize());
+  PRX_CUDA(h, cudaMemset(h->d_stats, 0, sizeof(DevStats)));
+  return PRX_OK;
+}
+
+int prx_get_stats(prx_handle* h, prx_stats* out)
+{
+  if (h == nullptr || out == nullptr) {
+    return PRX_ERR_BAD_ARG;
+  }
+  DeviceGuard g(h->device);
+  PRX_CUDA(h, cudaDeviceSynchronize());
+  DevStats s;
+  PRX_CUDA(h, cudaMemcpy(&s, h->d_stats, sizeof(s), cudaMemcpyDeviceToHost));
+  out->cells = (long long)s.v[ST_CELLS];
+  out->cells_masked = (long long)s.v[ST_MASKED];
+  out->n_steps = (long long)s.v[ST_STEPS];
+  out->n_rhs = (long long)s.v[ST_RHS];
+  out->n_jac = (long long)s.v[ST_JAC];
+  out->n_setups = (long long)s.v[ST_SETUPS];
+  out->n_newton = (long long)s.v[ST_NEWTON];
+  out->n_errfail = (long long)s.v[ST_ERRFAIL];
+  out->n_convfail = (long long)s.v[ST_CONVFAIL];
+  out->n_failed = (long long)s.v[ST_FAILED];
+  out->max_steps = (long long)s.v[ST_MAXSTEPS];
+  out->reserved = 0;
+  return PRX_OK;
+}
+
+int prx_last_react_return(prx_handle* h)
+{
+  if (h == nullptr) {
+    return PRX_ERR_BAD_ARG;
+  }
+  if (h->cfg.reactor_kind == PRX_REACTOR_CVODE) {
+    return 20; // ReactorCvode.cpp:1463-1464: "Dummy, the return value is no longer used"
+  }
+  DeviceGuard g(h->device);
+  if (cudaDeviceSynchronize() != cudaSuccess || h->last_ncells <= 0) {
+    return 0;
+  }
+  unsigned long long v = 0;
+  if (cudaMemcpy(&v, &h->d_stats->v[ST_LAST_STEPS], sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    return 0;
+  }
+  return (int)((double)v / (double)h->last_ncells); // ReactorRK64.cpp:316-319
+}
+
+int prx_probe_rhs_host(
+  prx_handle* h, int n, double t, const double* y, const double* rhoe, const double* rhoesrc,
+  const double* rYsrc, double* ydot)
+{
+  if (h == nullptr || n <= 0 || !y || !rhoe || !rhoesrc || !rYsrc || !ydot) {
+    return PRX_ERR_BAD_ARG;
+  }
+  DeviceGuard g(h->device);
+  const int N = h->ops->num_species, NEQ = N + 1;
+  const size_t nd = (size_t)n * (2 * NEQ + N + 2);
+  const int rc = ensure_stage(h, nd * sizeof(double));
+  if (rc != PRX_OK) {
+    return rc;
+  }
+  double* d_y = h->d_stage;
+  double* d_yd = d_y + (size_t)n * NEQ;
+  double* d_src = d_yd + (size_t)n * NEQ;
+  double* d_e = d_src + (size_t)n * N;
+  double* d_es = d_e + n;
+  cudaStream_t st = h->stage_stream;
+  PRX_CUDA(h, cudaMemcpyAsync(d_y, y, sizeof(double) * n * NEQ, cudaMemcpyHostToDevice, st));
+  PRX_CUDA(h, cudaMemcpyAsync(d_src, rYsrc, sizeof(double) * n * N, cudaMemcpyHostToDevice, st));
+  PRX_CUDA(h, cudaMemcpyAsync(d_e, rhoe, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  PRX_CUDA(h, cudaMemcpyAsync(d_es, rhoesrc, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  PRX_CUDA(h, h->ops->probe_rhs(n, t, h->cfg.reactor_type, d_y, d_e, d_es, d_src, d_yd, st));
+  PRX_CUDA(h, cudaMemcpyAsync(ydot, d_yd, sizeof(double) * n * NEQ, cudaMemcpyDeviceToHost, st));
+  PRX_CUDA(h, cudaStreamSynchronize(st));
+  return PRX_OK;
+}
+
+int prx_probe_jac_host(prx_handle* h, int n, const double* y, double* J)
+{
+  if (h == nullptr || n <= 0 || !y || !J) {
+    return PRX_ERR_BAD_ARG;
+  }
+  DeviceGuard g(h->device);
+  const int N = h->ops->num_species, NEQ = N + 1;
+  const size_t nd = (size_t)n * (NEQ + (size_t)NEQ * NEQ);
+  const int rc = ensure_stage(h, nd * sizeof(double));
+  if (rc != PRX_OK) {
+    return rc;
+  }
+  double* d_y = h->d_stage;
+  double* d_J = d_y + (size_t)n * NEQ;
+  cudaStream_t st = h->stage_stream;
+  PRX_CUDA(h, cudaMemcpyAsync(d_y, y, sizeof(double) * n * NEQ, cudaMemcpyHostToDevice, st));
+  PRX_CUDA(h, h->ops->probe_jac(n, h->cfg.reactor_type, d_y, d_J, st));
+  PRX_CUDA(h, cudaMemcpyAsync(J, d_J, sizeof(double) * n * NEQ * NEQ, cudaMemcpyDeviceToHost, st));
+  PRX_CUDA(h, cudaStreamSynchronize(st));
+  return PRX_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,184 @@
+// prx_chem.cuh - per-cell thermo-chemistry on the device: the EOS facade and the ODE
+// right-hand side, layered on the generated mechanism header (gen/mech_<mech>.cuh).
+//
+// Reference functions restated here (PP = PelePhysics):
+//   GET_T_GIVEN_EY / GET_T_GIVEN_HY   PP/Mechanisms/LiDryer/mechanism.H:1419-1520
+//   CKUMS / CKHMS / CKYTCR / CKWC     mechanism.H:2019-2043, 1785-1796, 2606-2623
+//   Fuego::RTY2WDOT / RTY2JAC         PP/Source/Eos/Fuego.H:234-266 (+DWDOT mechanism.H:5141-5162)
+//   utils::fKernelSpec                PP/Source/Reactions/ReactorUtils.H:358-415
+//   cvode::cJac (CPU flavour)         PP/Source/Reactions/ReactorCvodeJacobian.cpp:86-152
+//
+// One translation unit per mechanism (PRX_MECH_HEADER selects it), like the reference's
+// compile-time Chemistry_Model.  Everything is FP64; all per-cell vectors live in registers /
+// thread-local storage of the calling kernel.
+#ifndef PRX_CHEM_CUH
+#define PRX_CHEM_CUH
+
+#ifdef PRX_HOST_TEST
+// Host instantiation used ONLY by tests/host_harness (logic unit tests without a GPU).
+#include <cmath>
+#define PRX_DEVFN static inline
+#define PRX_DEVCONST static const
+#define PRX_DEV static inline
+#define PRX_DEV_NOINLINE static
+#else
+#define PRX_DEVFN __device__ __forceinline__
+#define PRX_DEVCONST static __constant__ const
+#define PRX_DEV __device__ __forceinline__
+#define PRX_DEV_NOINLINE __device__ __noinline__
+#endif
+
+#include PRX_MECH_HEADER
+
+#define PRX_N PRX_NUM_SPECIES
+#define PRX_NEQ (PRX_NUM_SPECIES + 1)
+
+namespace prx {
+
+constexpr int N = PRX_N;
+constexpr int NEQ = PRX_NEQ;
+
+// Newton solve of e(T,Y) = e (energy_type 1) or h(T,Y) = h (2): identical control flow to the
+// reference (bounds 90/4000 K with linear extrapolation, +-100 K clamp, break BEFORE the update).
+template <int ETYPE>
+PRX_DEV void t_from_energy(const double e, const double* y, double& t)
+{
+  const double tmin = PRX_TMIN, tmax = PRX_TMAX;
+  const double emin = (ETYPE == 1) ? ckubms(tmin, y) : ckhbms(tmin, y);
+  const double emax = (ETYPE == 1) ? ckubms(tmax, y) : ckhbms(tmax, y);
+  if (e < emin) {
+    const double cv = (ETYPE == 1) ? ckcvbs(tmin, y) : ckcpbs(tmin, y);
+    t = tmin - (emin - e) / cv;
+    return;
+  }
+  if (e > emax) {
+    const double cv = (ETYPE == 1) ? ckcvbs(tmax, y) : ckcpbs(tmax, y);
+    t = tmax - (emax - e) / cv;
+    return;
+  }
+  double t1 = t;
+  if (t1 < tmin || t1 > tmax) {
+    t1 = tmin + (tmax - tmin) / (emax - emin) * (e - emin);
+  }
+  for (int i = 0; i < 200; ++i) {
+    const double e1 = (ETYPE == 1) ? ckubms(t1, y) : ckhbms(t1, y);
+    const double cv = (ETYPE == 1) ? ckcvbs(t1, y) : ckcpbs(t1, y);
+    double dt = (e - e1) / cv;
+    if (dt > 100.) {
+      dt = 100.;
+    } else if (dt < -100.) {
+      dt = -100.;
+    } else if (fabs(dt) < 1.e-6) {
+      break;
+    }
+    t1 += dt;
+  }
+  t = t1;
+}
+
+PRX_DEV void t_from_energy(const int reactor_type, const double e, const double* y, double& t)
+{
+  if (reactor_type == 1) {
+    t_from_energy<1>(e, y, t);
+  } else {
+    t_from_energy<2>(e, y, t);
+  }
+}
+
+// Per-cell constants of the ODE (CVODEUserData rhoe_init / rhoesrc_ext / rYsrc_ext,
+// PP/Source/Reactions/ReactorCvodeUtils.H:34-100)
+struct CellSrc
+{
+  double rhoe_init;
+  double rhoesrc;
+  double rYsrc[N];
+};
+
+// ODE right-hand side for one cell: y = (rhoY_0..rhoY_{N-1}, T) -> ydot.
+PRX_DEV void rhs(const double t, const int reactor_type, const double* y, double* ydot, const CellSrc& c)
+{
+  double rho = 0.0;
+  double Y[N];
+#pragma unroll
+  for (int n = 0; n < N; n++) {
+    rho += y[n];
+  }
+  const double rho_inv = 1.0 / rho;
+#pragma unroll
+  for (int n = 0; n < N; n++) {
+    Y[n] = y[n] * rho_inv;
+  }
+  const double nrg = (c.rhoe_init + c.rhoesrc * t) * rho_inv;
+  double temp = y[N];
+  double Cv;
+  double ei[N];
+  const double RT_unused = 0.0;
+  (void)RT_unused;
+  if (reactor_type == 1) {
+    t_from_energy<1>(nrg, Y, temp);
+    e_RT_fn(ei, temp);
+    Cv = ckcvbs(temp, Y);
+  } else {
+    t_from_energy<2>(nrg, Y, temp);
+    h_RT_fn(ei, temp);
+    Cv = ckcpbs(temp, Y);
+  }
+  const double RT = PRX_RU * temp;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    ei[i] *= RT * prx_imw[i];
+  }
+  // RTY2WDOT: C = rho*Y/W (CGS) -> SI -> production_rate -> CGS -> mass rates
+  double C[N], wdot[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    C[i] = rho * Y[i] * prx_imw[i];
+    C[i] *= 1.0e6;
+  }
+  production_rate(wdot, C, temp);
+  double rhoesrc = c.rhoesrc;
+#pragma unroll
+  for (int n = 0; n < N; n++) {
+    double w = wdot[n] * 1.0e-6;
+    w *= prx_mw[n];
+    const double cdot_rYs = w + c.rYsrc[n];
+    ydot[n] = cdot_rYs;
+    rhoesrc -= cdot_rYs * ei[n];
+  }
+  ydot[N] = rhoesrc * (rho_inv / Cv);
+}
+
+// Analytic Jacobian of the ODE in (rhoY, T) variables, written through the accessor
+// JM(row, col) (= d f_row / d y_col).  Scratch Jt is NEQ*NEQ doubles, column-major.
+template <class Store>
+PRX_DEV void jac_analytic(const int reactor_type, const double* ydata, double* Jt, Store&& JM)
+{
+  double rho = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    rho = rho + ydata[i];
+  }
+  const double temp = ydata[N];
+  double c[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    const double Yi = ydata[i] / rho;
+    c[i] = 1.e6 * (rho * Yi * prx_imw[i]);
+  }
+  const int consP = (reactor_type == 2);
+  ajacobian(Jt, c, temp, consP);
+  // DWDOT unit conversion (SI <-> CGS) and the cJac scaling between C and rhoY variables
+  for (int i = 0; i < N; i++) {
+    for (int k = 0; k < N; k++) {
+      JM(k, i, Jt[i * NEQ + k] * prx_mw[k] * prx_imw[i]);
+    }
+    JM(N, i, (Jt[i * NEQ + N] * 1.e6) * prx_imw[i]);
+  }
+  for (int i = 0; i < N; i++) {
+    JM(i, N, (Jt[N * NEQ + i] * 1.e-6) * prx_mw[i]);
+  }
+  JM(N, N, Jt[N * NEQ + N]);
+}
+
+} // namespace prx
+#endif

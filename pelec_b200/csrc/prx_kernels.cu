@@ -1,0 +1,511 @@
+// prx_kernels.cu - the sm_100a kernels of the reactor; compiled ONCE PER MECHANISM with
+//   -DPRX_MECH_HEADER="gen/mech_<mech>.cuh" -DPRX_MECH_SUFFIX=<mech>
+//
+// Kernel anatomy (both reactors): a PERSISTENT grid (a multiple of the 148 SMs) whose warps
+// loop over three phases until the box's work queue is empty:
+//   (1) refill   lanes without a cell take the next cell indices from a global atomic queue
+//                (warp-aggregated: one atomicAdd per warp per refill).  Cells are handed out
+//                in index order, so a warp's loads/stores of the SoA arrays stay mostly
+//                coalesced along i and neighbouring (similarly stiff) cells share a warp.
+//                This is the active-cell compaction: a lane never idles because its cell
+//                finished early, it just starts the next one.
+//   (2) control  every lane runs its integrator coroutine (prx_integrators.cuh) up to the
+//                next expensive request - cheap, divergent FP64 vector code.
+//   (3) serve    the warp executes each kind of request (RHS / Jacobian / LU) once, at a
+//                converged call site, for all lanes that asked.  Rare kinds can be deferred
+//                until several lanes ask (SchedParams), which does not change any cell's
+//                arithmetic, only when it happens.
+// HBM traffic is only the boundary arrays: (2N+3) doubles in, (N+3) out per cell.
+#include <cstdio>
+
+#include "prx_integrators.cuh"
+#include "prx_kernels.cuh"
+
+#ifndef PRX_BLOCK
+#define PRX_BLOCK 128
+#endif
+
+#define PRX_CAT2(a, b) a##b
+#define PRX_CAT(a, b) PRX_CAT2(a, b)
+
+namespace prx {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+struct LaneStats
+{
+  unsigned long long cells, masked, steps, rhs, jac, setups, newton, errfail, convfail, failed, maxsteps;
+};
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v += __shfl_xor_sync(FULL, v, o);
+  }
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_max(unsigned long long v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long w = __shfl_xor_sync(FULL, v, o);
+    v = w > v ? w : v;
+  }
+  return v;
+}
+
+__device__ __forceinline__ void flush_stats(const LaneStats& ls, DevStats* st)
+{
+  const unsigned lane = threadIdx.x & 31;
+  unsigned long long v[11] = {ls.cells, ls.masked, ls.steps, ls.rhs, ls.jac, ls.setups,
+                              ls.newton, ls.errfail, ls.convfail, ls.failed, 0ull};
+#pragma unroll
+  for (int i = 0; i < 10; i++) {
+    v[i] = warp_sum(v[i]);
+  }
+  const unsigned long long mx = warp_max(ls.maxsteps);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+      if (v[i]) {
+        atomicAdd(&st->v[i], v[i]);
+      }
+    }
+    atomicMax(&st->v[ST_MAXSTEPS], mx);
+    atomicAdd(&st->v[ST_LAST_STEPS], v[2]);
+  }
+}
+
+// warp-aggregated fetch of the next cell indices; returns -1 when the queue is empty
+__device__ __forceinline__ int fetch_cell(const bool need, int* queue, const int ncells)
+{
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned m = __ballot_sync(FULL, need);
+  if (m == 0) {
+    return -1;
+  }
+  int base = 0;
+  const int leader = __ffs(m) - 1;
+  if (lane == leader) {
+    base = atomicAdd(queue, __popc(m));
+  }
+  base = __shfl_sync(FULL, base, leader);
+  if (!need) {
+    return -1;
+  }
+  const int idx = base + __popc(m & ((1u << lane) - 1u));
+  return (idx < ncells) ? idx : -2; // -2: exhausted
+}
+
+__device__ __forceinline__ long long cell_offset(const int c, const int* len, const long long js, const long long ks)
+{
+  const int i = c % len[0];
+  const int r = c / len[0];
+  const int j = r % len[1];
+  const int k = r / len[1];
+  return (long long)i + (long long)j * js + (long long)k * ks;
+}
+
+// ---- boundary loads / stores ---------------------------------------------------------
+// Array4: SoA, consecutive lanes <-> consecutive i: every component load is a coalesced
+// 256-byte warp transaction.  Flat (YCOrder): cell-major, used by the 1-D react() only.
+__device__ __forceinline__ bool load_cell(
+  const BoxArgs& a, const int c, double* y /*NEQ*/, CellSrc& src, const int clean_init_massfrac)
+{
+  if (a.layout == LAYOUT_ARRAY4) {
+    if (a.mask.p != nullptr) {
+      if (a.mask.p[cell_offset(c, a.len, a.mask.js, a.mask.ks)] == -1) {
+        return false;
+      }
+    }
+    const long long o = cell_offset(c, a.len, a.rY.js, a.rY.ks);
+    const long long os = cell_offset(c, a.len, a.rYsrc.js, a.rYsrc.ks);
+    double rho_old = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      y[k] = __ldg(a.rY.p + o + k * a.rY.ns);
+      src.rYsrc[k] = __ldg(a.rYsrc.p + os + k * a.rYsrc.ns);
+      rho_old += y[k];
+    }
+    if (clean_init_massfrac) { // ReactorUtils.H:183-199
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        y[k] = fmin(fmax(0.0, y[k]), rho_old);
+      }
+    }
+    y[N] = a.T.p[cell_offset(c, a.len, a.T.js, a.T.ks)];
+    src.rhoe_init = a.rE.p[cell_offset(c, a.len, a.rE.js, a.rE.ks)];
+    src.rhoesrc = a.rEsrc.p[cell_offset(c, a.len, a.rEsrc.js, a.rEsrc.ks)];
+  } else {
+#pragma unroll
+    for (int k = 0; k < NEQ; k++) {
+      y[k] = a.y[(long long)c * NEQ + k];
+    }
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      src.rYsrc[k] = a.ysrc[(long long)c * N + k];
+    }
+    src.rhoe_init = a.e[c];
+    src.rhoesrc = a.esrc[c];
+  }
+  return true;
+}
+
+__device__ __forceinline__ void store_masked(const BoxArgs& a, const int c)
+{
+  a.FC.p[cell_offset(c, a.len, a.FC.js, a.FC.ks)] = 0.0;
+}
+
+// box_unflatten (ReactorUtils.H:222-291) / RK64 write-back (ReactorRK64.cpp:290-309)
+__device__ __forceinline__ void store_cell(
+  const BoxArgs& a, const int c, const double* y /*NEQ: rhoY_new, T (pre re-solve)*/, const CellSrc& src,
+  const int reactor_type, const double fc, const int clean_init_massfrac, const bool resolve_T)
+{
+  const double rhoe_out = src.rhoe_init + a.dt * src.rhoesrc;
+  if (a.layout == LAYOUT_ARRAY4) {
+    const long long o = cell_offset(c, a.len, a.rY.js, a.rY.ks);
+    double ynew[N];
+    double rho = 0.0;
+    if (clean_init_massfrac) {
+      // new rhoY = old + CVODE increment measured against the clipped input (ReactorUtils.H:244-271)
+      double rho_old = 0.0, rho_oldclipped = 0.0;
+      double yold[N];
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        yold[k] = a.rY.p[o + k * a.rY.ns];
+        rho_old += yold[k];
+      }
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        rho_oldclipped += fmin(fmax(0.0, yold[k]), rho_old);
+      }
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        const double clipped = fmin(fmax(0.0, yold[k]), rho_old);
+        ynew[k] = yold[k] + (y[k] - clipped) * rho_old / rho_oldclipped;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        ynew[k] = y[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      a.rY.p[o + k * a.rY.ns] = ynew[k];
+      rho += ynew[k];
+    }
+    double temp = y[N];
+    if (resolve_T) {
+      const double rho_inv = 1.0 / rho;
+      double Y[N];
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        Y[k] = ynew[k] * rho_inv;
+      }
+      t_from_energy(reactor_type, rhoe_out * rho_inv, Y, temp);
+    }
+    a.rE.p[cell_offset(c, a.len, a.rE.js, a.rE.ks)] = rhoe_out;
+    a.T.p[cell_offset(c, a.len, a.T.js, a.T.ks)] = temp;
+    a.FC.p[cell_offset(c, a.len, a.FC.js, a.FC.ks)] = fc;
+  } else {
+#pragma unroll
+    for (int k = 0; k < NEQ; k++) {
+      a.y[(long long)c * NEQ + k] = y[k];
+    }
+    a.e[c] = rhoe_out;
+    if (a.fc != nullptr) {
+      a.fc[c] = fc;
+    }
+  }
+}
+
+// =====================================================================================
+// RK64 kernel
+// =====================================================================================
+__global__ void __launch_bounds__(PRX_BLOCK) PRX_CAT(rk64_kernel_, PRX_MECH_SUFFIX)(
+  const BoxArgs a, const Rk64Params p, int* __restrict__ queue, DevStats* __restrict__ stats)
+{
+  Rk64Cell s;
+  int cell = -1;
+  bool exhausted = false;
+  int req = REQ_NONE;
+  LaneStats ls = {};
+  for (;;) {
+    const int got = fetch_cell((cell < 0) && !exhausted, queue, a.ncells);
+    if (got == -2) {
+      exhausted = true;
+    } else if (got >= 0) {
+      cell = got;
+      load_cell(a, cell, s.soln, s.src, 0); // RK64 ignores the mask (reference: /*mask*/ unused)
+      rk64_begin(s, p, a.dt, a.time);
+      req = REQ_NONE;
+    }
+    if (__all_sync(FULL, exhausted && (cell < 0))) {
+      break;
+    }
+    if (cell >= 0 && req == REQ_NONE) {
+      req = rk64_resume(s, p);
+    }
+    if (req == REQ_RHS) {
+      rhs(s.t_eval, p.reactor_type, s.soln, s.ydot, s.src);
+      req = REQ_NONE;
+    }
+    if (req == REQ_DONE) {
+      // the write-back re-solves T from (e_out, Y_out) with the integrated T as the guess
+      store_cell(a, cell, s.soln, s.src, p.reactor_type, double(s.nsteps), 0, p.array4_semantics != 0);
+      ls.cells++;
+      ls.steps += s.nsteps;
+      ls.rhs += 6ull * s.nsteps;
+      ls.maxsteps = (unsigned long long)s.nsteps > ls.maxsteps ? s.nsteps : ls.maxsteps;
+      cell = -1;
+      req = REQ_NONE;
+    }
+  }
+  flush_stats(ls, stats);
+}
+
+// =====================================================================================
+// BDF (CVODE-per-cell) kernel
+// =====================================================================================
+__device__ __forceinline__ double* bdf_vec(BdfCell& s, const int sel)
+{
+  switch (sel) {
+  case V_ZN0:
+    return s.zn[0];
+  case V_ZN1:
+    return s.zn[1];
+  case V_Y:
+    return s.y;
+  case V_TEMPV:
+    return s.tempv;
+  default:
+    return s.ftemp;
+  }
+}
+
+__global__ void __launch_bounds__(PRX_BLOCK) PRX_CAT(bdf_kernel_, PRX_MECH_SUFFIX)(
+  const BoxArgs a, const BdfParams p, const SchedParams sp, int* __restrict__ queue,
+  DevStats* __restrict__ stats)
+{
+  BdfCell s;
+  int cell = -1;
+  bool exhausted = false;
+  int req = REQ_NONE;
+  LaneStats ls = {};
+  for (;;) {
+    // ---- (1) refill ----
+    const int got = fetch_cell((cell < 0) && !exhausted, queue, a.ncells);
+    if (got == -2) {
+      exhausted = true;
+    } else if (got >= 0) {
+      if (load_cell(a, got, s.zn[0], s.src, p.clean_init_massfrac)) {
+        cell = got;
+        bdf_begin(s, p, a.dt, a.time);
+        req = REQ_NONE;
+      } else {
+        store_masked(a, got); // mask == -1: FC = 0, nothing else touched (ReactorCvode.cpp:1451-1453)
+        ls.masked++;
+      }
+    }
+    if (__all_sync(FULL, exhausted && (cell < 0))) {
+      break;
+    }
+    // ---- (2) control ----
+    if (cell >= 0 && req == REQ_NONE) {
+      req = bdf_resume(s, p);
+    }
+    // ---- (3) serve ----
+    const unsigned m_rhs = __ballot_sync(FULL, req == REQ_RHS);
+    const unsigned m_jac = __ballot_sync(FULL, req == REQ_JAC);
+    const unsigned m_lu = __ballot_sync(FULL, req == REQ_LU);
+    if (req == REQ_RHS) {
+      rhs(s.t_eval, p.reactor_type, bdf_vec(s, s.in_sel), bdf_vec(s, s.out_sel), s.src);
+      req = REQ_NONE;
+    }
+    if (m_jac && ((__popc(m_jac) >= sp.jac_defer_min_lanes) || (m_rhs == 0))) {
+      if (req == REQ_JAC) {
+        double* A = s.A;
+        // savedJ is free here (it is overwritten with the new J right after): use it as scratch
+        jac_analytic(p.reactor_type, s.y, s.savedJ, [A](const int row, const int col, const double v) {
+          A[col * NEQ + row] = v;
+        });
+        req = REQ_NONE;
+      }
+    }
+    if (m_lu && ((__popc(m_lu) >= sp.lu_defer_min_lanes) || (m_rhs == 0))) {
+      if (req == REQ_LU) {
+        s.lu_info = dense_getrf(s.A, s.piv);
+        req = REQ_NONE;
+      }
+    }
+    if (req == REQ_DONE) {
+      store_cell(
+        a, cell, s.y, s.src, p.reactor_type, double(s.nfe + s.nfeDQ), p.clean_init_massfrac,
+        p.array4_semantics != 0);
+      ls.cells++;
+      ls.steps += s.nst;
+      ls.rhs += s.nfe + s.nfeDQ;
+      ls.jac += s.nje;
+      ls.setups += s.nsetups;
+      ls.newton += s.nni;
+      ls.errfail += s.netf;
+      ls.convfail += s.ncfn;
+      ls.failed += (s.flag != CV_SUCCESS);
+      ls.maxsteps = (unsigned long long)s.nst > ls.maxsteps ? s.nst : ls.maxsteps;
+      cell = -1;
+      req = REQ_NONE;
+    }
+  }
+  flush_stats(ls, stats);
+}
+
+// =====================================================================================
+// probes (parity tests of the device thermo-chemistry)
+// =====================================================================================
+__global__ void PRX_CAT(probe_rhs_kernel_, PRX_MECH_SUFFIX)(
+  const int n, const double t, const int reactor_type, const double* __restrict__ y,
+  const double* __restrict__ rhoe, const double* __restrict__ rhoesrc, const double* __restrict__ rYsrc,
+  double* __restrict__ ydot)
+{
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) {
+    return;
+  }
+  double yy[NEQ], yd[NEQ];
+  CellSrc src;
+  for (int k = 0; k < NEQ; k++) {
+    yy[k] = y[(long long)s * NEQ + k];
+  }
+  for (int k = 0; k < N; k++) {
+    src.rYsrc[k] = rYsrc[(long long)s * N + k];
+  }
+  src.rhoe_init = rhoe[s];
+  src.rhoesrc = rhoesrc[s];
+  rhs(t, reactor_type, yy, yd, src);
+  for (int k = 0; k < NEQ; k++) {
+    ydot[(long long)s * NEQ + k] = yd[k];
+  }
+}
+
+__global__ void PRX_CAT(probe_jac_kernel_, PRX_MECH_SUFFIX)(
+  const int n, const int reactor_type, const double* __restrict__ y, double* __restrict__ J,
+  double* __restrict__ scratch)
+{
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) {
+    return;
+  }
+  double yy[NEQ];
+  for (int k = 0; k < NEQ; k++) {
+    yy[k] = y[(long long)s * NEQ + k];
+  }
+  double* Jt = scratch + (long long)s * NEQ * NEQ;
+  double* Jo = J + (long long)s * NEQ * NEQ;
+  jac_analytic(reactor_type, yy, Jt, [Jo](const int row, const int col, const double v) { Jo[col * NEQ + row] = v; });
+}
+
+// =====================================================================================
+// launchers
+// =====================================================================================
+int persistent_grid(const void* kernel, const int ncells)
+{
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, PRX_BLOCK, 0) != cudaSuccess || per_sm < 1) {
+    per_sm = 1;
+  }
+  long long grid = (long long)sms * per_sm; // a multiple of the SM count: one full wave, persistent
+  const long long needed = ((long long)ncells + PRX_BLOCK - 1) / PRX_BLOCK;
+  if (needed < grid) {
+    grid = needed;
+  }
+  return (int)(grid < 1 ? 1 : grid);
+}
+
+cudaError_t launch_rk64(const BoxArgs& a, const prx_config& cfg, int* queue, DevStats* stats, cudaStream_t stream)
+{
+  if (a.ncells <= 0) {
+    return cudaSuccess;
+  }
+  Rk64Params p;
+  p.reactor_type = cfg.reactor_type;
+  p.atol = cfg.atol;
+  p.nsub_guess = cfg.rk64_nsubsteps_guess;
+  p.nsub_min = cfg.rk64_nsubsteps_min;
+  p.nsub_max = cfg.rk64_nsubsteps_max;
+  p.array4_semantics = (a.layout == LAYOUT_ARRAY4);
+  auto kern = PRX_CAT(rk64_kernel_, PRX_MECH_SUFFIX);
+  const int grid = persistent_grid((const void*)kern, a.ncells);
+  cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(int), stream);
+  if (e != cudaSuccess) {
+    return e;
+  }
+  kern<<<grid, PRX_BLOCK, 0, stream>>>(a, p, queue, stats);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bdf(
+  const BoxArgs& a, const prx_config& cfg, const double* typ_vals, int* queue, DevStats* stats,
+  const SchedParams& sp, cudaStream_t stream)
+{
+  if (a.ncells <= 0) {
+    return cudaSuccess;
+  }
+  BdfParams p;
+  p.reactor_type = cfg.reactor_type;
+  p.rtol = cfg.rtol;
+  for (int k = 0; k < NEQ; k++) {
+    p.atolv[k] = (typ_vals != nullptr && typ_vals[0] > 0.0) ? typ_vals[k] * cfg.atol : cfg.atol;
+  }
+  p.qmax = cfg.max_order;
+  p.maxcor = cfg.max_nls_iters;
+  p.analytic_jac = (cfg.solve_type == PRX_SOLVE_DENSE_AJ_DIRECT);
+  p.mxstep = 10000;
+  p.maxnef = 100;
+  p.msbj = 100;
+  p.clean_init_massfrac = cfg.clean_init_massfrac;
+  p.array4_semantics = (a.layout == LAYOUT_ARRAY4);
+  auto kern = PRX_CAT(bdf_kernel_, PRX_MECH_SUFFIX);
+  const int grid = persistent_grid((const void*)kern, a.ncells);
+  cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(int), stream);
+  if (e != cudaSuccess) {
+    return e;
+  }
+  kern<<<grid, PRX_BLOCK, 0, stream>>>(a, p, sp, queue, stats);
+  return cudaGetLastError();
+}
+
+cudaError_t probe_rhs(
+  int n, double t, int reactor_type, const double* y, const double* rhoe, const double* rhoesrc,
+  const double* rYsrc, double* ydot, cudaStream_t stream)
+{
+  PRX_CAT(probe_rhs_kernel_, PRX_MECH_SUFFIX)<<<(n + 63) / 64, 64, 0, stream>>>(
+    n, t, reactor_type, y, rhoe, rhoesrc, rYsrc, ydot);
+  return cudaGetLastError();
+}
+
+cudaError_t probe_jac(int n, int reactor_type, const double* y, double* J, cudaStream_t stream)
+{
+  double* scratch = nullptr;
+  cudaError_t e = cudaMalloc(&scratch, sizeof(double) * (size_t)n * NEQ * NEQ);
+  if (e != cudaSuccess) {
+    return e;
+  }
+  PRX_CAT(probe_jac_kernel_, PRX_MECH_SUFFIX)<<<(n + 63) / 64, 64, 0, stream>>>(n, reactor_type, y, J, scratch);
+  e = cudaGetLastError();
+  cudaStreamSynchronize(stream);
+  cudaFree(scratch);
+  return e;
+}
+
+const MechOps g_ops = {PRX_NUM_SPECIES, PRX_NUM_REACTIONS, PRX_MECH_NAME, launch_rk64, launch_bdf, probe_rhs, probe_jac};
+
+} // namespace
+
+const MechOps* PRX_CAT(mech_ops_, PRX_MECH_SUFFIX)() { return &g_ops; }
+
+} // namespace prx

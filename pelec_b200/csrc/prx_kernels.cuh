@@ -1,0 +1,82 @@
+// prx_kernels.cuh - shared declarations between the per-mechanism kernel translation units
+// (prx_kernels.cu, compiled once per mechanism) and the mechanism-independent C ABI (prx_api.cu).
+#ifndef PRX_KERNELS_CUH
+#define PRX_KERNELS_CUH
+
+#include <cuda_runtime.h>
+
+#include "../../include/pelerx_b200.h"
+
+namespace prx {
+
+// One of the seven arrays crossing the reactor boundary, already reduced to what a kernel
+// needs: base pointer of cell (lo) component 0, and strides in elements.
+struct ArrView
+{
+  double* p;
+  long long js, ks, ns;
+};
+struct ArrViewI
+{
+  const int* p;
+  long long js, ks, ns;
+};
+
+enum Layout { LAYOUT_ARRAY4 = 0, LAYOUT_FLAT = 1 };
+
+struct BoxArgs
+{
+  int layout;
+  int ncells;
+  int len[3];
+  // Array4 layout
+  ArrView rY, rYsrc, T, rE, rEsrc, FC;
+  ArrViewI mask; // p == nullptr: no mask
+  // flat layout (YCOrder): y[c*(N+1)+k], ysrc[c*N+k], e[c], esrc[c], fc[c]
+  double* y;
+  const double* ysrc;
+  double* e;
+  const double* esrc;
+  double* fc;
+  double dt, time;
+};
+
+// device-side counters (unsigned long long so that atomicAdd applies)
+struct DevStats
+{
+  unsigned long long v[12];
+};
+enum StatIdx {
+  ST_CELLS = 0, ST_MASKED, ST_STEPS, ST_RHS, ST_JAC, ST_SETUPS, ST_NEWTON, ST_ERRFAIL, ST_CONVFAIL,
+  ST_FAILED, ST_MAXSTEPS, ST_LAST_STEPS
+};
+
+// scheduling knobs of the warp loop (see prx_kernels.cu)
+struct SchedParams
+{
+  int jac_defer_min_lanes; // serve REQ_JAC only when >= this many lanes ask (or nobody has RHS work)
+  int lu_defer_min_lanes;
+};
+
+struct MechOps
+{
+  int num_species;
+  int num_reactions;
+  const char* name;
+  // launchers; all asynchronous on `stream`
+  cudaError_t (*launch_rk64)(const BoxArgs&, const prx_config&, int* queue, DevStats* stats, cudaStream_t stream);
+  cudaError_t (*launch_bdf)(
+    const BoxArgs&, const prx_config&, const double* typ_vals_host, int* queue, DevStats* stats,
+    const SchedParams&, cudaStream_t stream);
+  cudaError_t (*probe_rhs)(
+    int n, double t, int reactor_type, const double* y, const double* rhoe, const double* rhoesrc,
+    const double* rYsrc, double* ydot, cudaStream_t stream);
+  cudaError_t (*probe_jac)(int n, int reactor_type, const double* y, double* J, cudaStream_t stream);
+};
+
+const MechOps* mech_ops_LiDryer();
+const MechOps* mech_ops_drm19();
+const MechOps* mech_ops_dodecane_lu();
+
+} // namespace prx
+#endif

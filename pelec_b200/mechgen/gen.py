@@ -69,7 +69,7 @@ class Emitter:
         self.fl = flavour
         self.N = len(d["species"])
         self.L = []
-        self.q = "__device__ __forceinline__ " if flavour == "cuda" else "static inline "
+        self.q = "PRX_DEVFN " if flavour == "cuda" else "static inline "
 
     def w(self, s=""):
         self.L.append(s)
@@ -515,6 +515,11 @@ class Emitter:
         w("#define %s" % guard)
         if self.fl == "c":
             w("#include <math.h>")
+        else:
+            w("#ifndef PRX_DEVFN")
+            w("#define PRX_DEVFN __device__ __forceinline__")
+            w("#define PRX_DEVCONST __device__ static const")
+            w("#endif")
         w("#ifndef PRX_RESTRICT")
         w("#define PRX_RESTRICT %s" % ("__restrict__"))
         w("#endif")
@@ -528,7 +533,7 @@ class Emitter:
         w("#ifndef PRX_J")
         w("#define PRX_J(row, col) J[(col) * %d + (row)]" % (N + 1))
         w("#endif")
-        cq = "__device__ static const" if self.fl == "cuda" else "static const"
+        cq = "PRX_DEVCONST" if self.fl == "cuda" else "static const"
         w("%s double prx_mw[%d] = {%s};" % (cq, N, ", ".join(d["mw"])))
         w("%s double prx_imw[%d] = {%s};" % (cq, N, ", ".join(d["imw"])))
         if self.fl == "c":
@@ -580,3 +585,59 @@ if __name__ == "__main__":
     root = os.path.abspath(os.path.join(HERE, "..", ".."))
     for p in generate_all(root, tuple(sys.argv[1:]) or ("LiDryer", "drm19", "dodecane_lu")):
         print(os.path.relpath(p, root), os.path.getsize(p), "bytes")
+
+
+# ---------------------------------------------------------------------------------------------
+# Algorithmic operation counts of the generated code (the FLOP model of bench.py / DESIGN.md)
+# ---------------------------------------------------------------------------------------------
+def _function_bodies(text):
+    import re
+    out = {}
+    for m in re.finditer(r"^PRX_DEVFN (?:void|double) (\w+)\([^)]*\)\n\{\n(.*?)\n\}\n", text, re.S | re.M):
+        out[m.group(1)] = m.group(2)
+    return out
+
+
+def _count(body):
+    import re
+    body = re.sub(r"//.*", "", body)
+    trans = len(re.findall(r"\b(?:exp|log10|log)\(", body))
+    # binary arithmetic operators (unary signs of literals are not operations)
+    arith = len(re.findall(r"(?<=[\w\)\]]) [-+*/] (?=[\w\(\-])", body)) + len(re.findall(r"[-+*/]=", body))
+    return arith, trans
+
+
+def op_counts(mech):
+    """{'F_rhs', 'T_rhs', 'F_jac', 'T_jac', 'F_lu', 'F_slv', 'F_vec', ...}: arithmetic operations (+,-,*,/ = 1)
+    and transcendental calls (exp/log/log10, listed separately and costed at 1 flop in the algorithmic figure,
+    SURVEY.md 8d) of ONE evaluation, counted on the text the generator emits (consP = 0 branch of the
+    Jacobian).  T-Newton: 2 bound evaluations + 3 polynomial passes (2 updates + the pass that breaks)."""
+    d = load(mech)
+    N = len(d["species"])
+    neq = N + 1
+    text = emit(mech, "cuda")
+    fb = _function_bodies(text)
+    # thermo functions carry both temperature ranges; only one branch executes
+    def one_branch(body):
+        return re.sub(r"\} else \{.*?\n  \}", "}", body, flags=re.S)
+    import re
+    c = {k: _count(one_branch(v) if k not in ("production_rate", "ajacobian") else v) for k, v in fb.items()}
+    # the Jacobian text holds both consP branches; keep the generic part + the consP = 0 branch
+    import re
+    jb = fb["ajacobian"]
+    jb0 = re.sub(r"if \(consP\) \{.*?\} else \{", "{", jb, flags=re.S)
+    cj = _count(jb0)
+    newton_passes = 3
+    f_rhs = (c["production_rate"][0] + c["gibbs"][0] + (2 + newton_passes) * c["ckubms"][0]
+             + (newton_passes + 1) * c["ckcvbs"][0] + c["e_RT_fn"][0] + 12 * N)
+    t_rhs = c["production_rate"][1] + c["gibbs"][1]
+    f_jac = (cj[0] + c["gibbs"][0] + c["h_RT_fn"][0] + c["cv_R"][0] + c["dcvpRdT"][0] + c["e_RT_fn"][0]
+             + 3 * neq * neq + 2 * N * N + 8 * N)
+    t_jac = cj[1] + c["gibbs"][1]
+    return {
+        "N": N, "neq": neq, "reactions": len(d["reactions"]),
+        "F_rhs": f_rhs, "T_rhs": t_rhs, "F_jac": f_jac, "T_jac": t_jac,
+        "F_lu": round(2.0 / 3.0 * neq ** 3), "F_slv": 2 * neq * neq, "F_vec": 20 * neq,
+        "F_rk_update": 6 * 7 * neq,
+        "bytes_per_cell": (2 * N + 3) * 8 + (N + 3) * 8 + 4,
+    }

@@ -1,0 +1,130 @@
+"""CPU tests of the PRODUCT's host-side pieces that do not need a GPU:
+ - the C-ABI library loads and exports every symbol include/pelerx_b200.h declares;
+ - the mechanism generator is deterministic and complete;
+ - the resumable integrator state machines (pelec_b200/csrc/prx_integrators.cuh), instantiated
+   for the host by tests/host_harness, reproduce the oracle bit-for-bit (logic check without a GPU);
+ - argument checking / error codes of the entry points that return before touching the device."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from util import CVODE_SETTINGS, MECHS, ROOT, golden, golden_state
+
+from oracle.pyoracle import Oracle, _p, ip
+
+LIB = os.path.join(ROOT, "pelec_b200", "lib", "libpelerx_b200.so")
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "pelerx_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(prx_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(LIB):
+        pytest.fail("libpelerx_b200.so not built: run __graft_entry__.build()")
+    lib = C.CDLL(LIB)
+    syms = declared_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(lib, s), "missing export " + s
+    # and nothing else leaks out of the library
+    out = subprocess.check_output(["nm", "-D", "--defined-only", LIB]).decode()
+    exported = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    assert all(e.startswith("prx_") for e in exported), exported
+
+
+def test_metadata_and_argument_checks_without_device():
+    from pelec_b200 import reactor as R
+    lib = R.load_library()
+    assert lib.prx_num_species(0) == 9 and lib.prx_num_species(1) == 21 and lib.prx_num_species(2) == 53
+    assert lib.prx_num_reactions(0) == 21 and lib.prx_num_reactions(1) == 84 and lib.prx_num_reactions(2) == 268
+    assert lib.prx_mechanism_name(2) == b"dodecane_lu"
+    assert lib.prx_num_species(7) == -1
+    cfg = R.prx_config()
+    assert lib.prx_default_config(C.byref(cfg)) == 0
+    assert (cfg.rtol, cfg.atol, cfg.max_order, cfg.max_nls_iters) == (1e-6, 1e-10, 2, 3)
+    h = C.c_void_p()
+    bad = R.prx_config()
+    lib.prx_default_config(C.byref(bad))
+    bad.reactor_type = 3  # reference: amrex::Abort("Wrong reactor type...")
+    assert lib.prx_create(C.byref(bad), C.byref(h)) == -1
+    bad.reactor_type = 1
+    bad.solve_type = 9
+    assert lib.prx_create(C.byref(bad), C.byref(h)) == -4
+    bad.solve_type = 0
+    bad.mechanism = 11
+    assert lib.prx_create(C.byref(bad), C.byref(h)) == -1
+    import torch
+    if not torch.cuda.is_available():
+        # no CPU fallback: creating a reactor without a device must fail loudly
+        assert lib.prx_create(C.byref(cfg), C.byref(h)) == -2
+        with pytest.raises(R.PrxError):
+            r = R.ReactorB200.create("ReactorCvode", "LiDryer")
+            r.init(1, 1)
+    with pytest.raises(KeyError):
+        R.ReactorB200.create("ReactorFoo")
+    r = R.ReactorB200.create("ReactorCvode", "LiDryer", cvode__solve_type="GMRES")
+    with pytest.raises(R.PrxError):
+        r.init(1, 1)
+
+
+def test_generator_is_deterministic():
+    from pelec_b200.mechgen import gen
+    for m in MECHS:
+        a, b = gen.emit(m, "cuda"), gen.emit(m, "cuda")
+        assert a == b and "production_rate" in a and "ajacobian" in a
+        d = gen.load(m)
+        assert a.count("{ // R") == 2 * len(d["reactions"])
+
+
+@pytest.fixture(scope="module")
+def harness():
+    hdir = os.path.join(ROOT, "tests", "host_harness")
+    libs = {}
+    for m in MECHS:
+        so = os.path.join(hdir, "libhh_%s.so" % m)
+        src = os.path.join(hdir, "harness.cpp")
+        deps = [src] + [os.path.join(ROOT, "pelec_b200", "csrc", f) for f in
+                        ("prx_integrators.cuh", "prx_chem.cuh", "gen/mech_%s.cuh" % m)]
+        if not os.path.exists(deps[-1]):
+            from pelec_b200.mechgen import gen
+            gen.generate_all(ROOT, (m,))
+        if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17",
+                                   "-DPRX_MECH_HEADER=\"gen/mech_%s.cuh\"" % m,
+                                   "-I" + os.path.join(ROOT, "pelec_b200", "csrc"), "-o", so, src])
+        libs[m] = C.CDLL(so)
+    return libs
+
+
+@pytest.mark.parametrize("mech", MECHS)
+def test_state_machines_reproduce_oracle(harness, mech):
+    hh = harness[mech]
+    orc = Oracle(mech)
+    g = golden(mech)
+    dt = float(g["dt"])
+    for kw in CVODE_SETTINGS:
+        a, b = golden_state(g), golden_state(g)
+        a.mask[1::4] = -1
+        b.mask[1::4] = -1
+        so = orc.react_cvode(b, dt, want_stats=True, **kw)
+        stats = np.zeros((a.ncells, 8), dtype=np.int64)
+        hh.hh_react_cvode(C.c_int(1), C.c_double(kw["rtol"]), C.c_double(kw["atol"]), None, kw["max_order"], 3,
+                          1 if kw["solve_type"] == "denseAJ_direct" else 0, a.ncells, _p(a.rY), _p(a.rYsrc),
+                          _p(a.T), _p(a.rE), _p(a.rEsrc), _p(a.FC), a.mask.ctypes.data_as(ip), C.c_double(dt),
+                          C.c_double(0.0), stats.ctypes.data_as(C.POINTER(C.c_long)))
+        assert np.array_equal(a.rY, b.rY) and np.array_equal(a.T, b.T) and np.array_equal(a.FC, b.FC)
+        live = np.where(a.mask != -1)[0]
+        assert all(stats[i, 0] == so[i].nst and stats[i, 3] == so[i].nje and stats[i, 4] == so[i].nsetups for i in live)
+    if "rk64_rY" in g:
+        a, b = golden_state(g), golden_state(g)
+        orc.react_rk64(b, dt, atol=1e-10)
+        hh.hh_react_rk64(C.c_int(1), C.c_double(1e-10), 10, 5, 500, a.ncells, _p(a.rY), _p(a.rYsrc), _p(a.T),
+                         _p(a.rE), _p(a.rEsrc), _p(a.FC), C.c_double(dt), C.c_double(0.0))
+        assert np.array_equal(a.rY, b.rY) and np.array_equal(a.T, b.T) and np.array_equal(a.FC, b.FC)

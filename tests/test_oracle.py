@@ -1,0 +1,134 @@
+"""CPU tests (no GPU): the oracle restatement against (a) golden vectors produced by the unmodified
+reference, (b) the reference library itself when oracle/_ref is present, (c) the reference's own
+known answers (Jacobian FD self-check, PP/Testing/Exec/Jacobian/main.cpp:61-113)."""
+import numpy as np
+import pytest
+
+from util import CVODE_SETTINGS, MECHS, assert_cvode_parity, golden, golden_state, have_reference
+
+from oracle.pyoracle import Oracle, Reference, reacteval_states
+
+
+@pytest.fixture(scope="module", params=MECHS)
+def mech(request):
+    return request.param
+
+
+@pytest.fixture(scope="module")
+def orc(mech):
+    return Oracle(mech)
+
+
+def test_unit_vectors_match_golden(mech, orc):
+    g = golden(mech)
+    T, Y, rho, e = g["u_T"], g["u_Y"], g["u_rho"], g["u_e"]
+    r2, e2 = orc.pyt2re(np.full(len(T), 1013250.0), Y, T)
+    assert np.array_equal(r2, rho)
+    assert np.array_equal(e2, e)
+    ei, cv, em, hi = orc.thermo(T, Y)
+    # thermo, T-Newton, production rates and the full RHS are bit-exact restatements
+    assert np.array_equal(ei, g["u_ei"]) and np.array_equal(cv, g["u_cv"])
+    assert np.array_equal(em, g["u_emix"]) and np.array_equal(hi, g["u_hi"])
+    assert np.array_equal(orc.ey2t(e, Y, g["u_Tguess"]), g["u_Tsolve"])
+    assert np.array_equal(orc.rty2wdot(rho, T, Y), g["u_wdot"])
+    assert np.array_equal(orc.fkernelspec(1e-7, g["u_y"], rho * e, g["u_esrc"], g["u_src"]), g["u_ydot"])
+    # analytic Jacobian: same mathematics, own derivation -> agreement to rounding
+    J, Jr = orc.rty2jac(rho, T, Y), g["u_jac"]
+    sc = np.abs(Jr).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(J - Jr) / sc).max() < 1e-13
+
+
+def test_rk64_matches_golden(mech, orc):
+    g = golden(mech)
+    if "rk64_rY" not in g:
+        pytest.skip("reference RK64 is unstable (NaN) on these states")
+    s = golden_state(g)
+    orc.react_rk64(s, float(g["dt"]), atol=1e-10)
+    assert np.array_equal(s.rY, g["rk64_rY"]) and np.array_equal(s.T, g["rk64_T"])
+    assert np.array_equal(s.rE, g["rk64_rE"]) and np.array_equal(s.FC, g["rk64_FC"])
+
+
+@pytest.mark.parametrize("i", range(len(CVODE_SETTINGS)))
+def test_cvode_matches_golden(mech, orc, i):
+    g = golden(mech)
+    kw = CVODE_SETTINGS[i]
+    s = golden_state(g)
+    orc.react_cvode(s, float(g["dt"]), **kw)
+    if kw["solve_type"] == "dense_direct":
+        # difference-quotient Jacobian: every operation is a restatement -> bit-exact, FC included
+        assert np.array_equal(s.rY, g["cv%d_rY" % i]) and np.array_equal(s.T, g["cv%d_T" % i])
+        assert np.array_equal(s.FC, g["cv%d_FC" % i])
+    else:
+        # analytic Jacobian differs from the reference's at 1e-13 relative: results agree far
+        # inside the integrator tolerance, work counters may differ by a few RHS calls
+        assert_cvode_parity(s.rY, s.T, g["cv%d_rY" % i], g["cv%d_T" % i], kw["atol"], kw["rtol"])
+        dfc = np.abs(s.FC - g["cv%d_FC" % i])
+        fcmax = g["cv%d_FC" % i].max()
+        if fcmax < 200:
+            assert np.median(dfc) == 0 and dfc.max() <= max(8, 0.15 * fcmax)
+        else:  # hundreds of steps with error-test failures: the step sequence is chaotic in the last bits of J
+            assert dfc.max() <= 0.5 * fcmax
+    assert np.array_equal(s.rE, g["cv%d_rE" % i])
+
+
+def test_cvode_mask_matches_golden(mech, orc):
+    g = golden(mech)
+    s = golden_state(g)
+    s.mask[:] = g["cvmask_mask"]
+    orc.react_cvode(s, float(g["dt"]), **CVODE_SETTINGS[1])
+    skipped = g["cvmask_mask"] == -1
+    # masked cells: FC = 0 and nothing else touched (ReactorCvode.cpp:1407,1451-1453)
+    assert np.all(s.FC[skipped] == 0) and np.array_equal(s.rY[:, skipped], g["rY0"][:, skipped])
+    assert np.array_equal(s.T[skipped], g["T0"][skipped]) and np.array_equal(s.rE[skipped], g["rE0"][skipped])
+    assert np.abs(s.rY - g["cvmask_rY"]).max() <= 1e-9
+
+
+def test_jacobian_fd_selfcheck(mech, orc):
+    """The reference's own Jacobian test: species block of aJacobian vs central differences of the
+    production rates, ||err||^2/||J||^2 <= 1e-12 at T = 1000 K (PP/Testing/Exec/Jacobian/main.cpp:61-113)."""
+    rng = np.random.default_rng(42)
+    N = orc.N
+    T = np.array([1000.0])
+    C = (rng.random((1, N)) + 1e-4) * 1e-6  # the reference draws sc in [1e-4, 1] mol/m^3; here mol/cm^3
+    rho = (C * orc.mw[None, :]).sum(axis=1)
+    Y = C * orc.mw[None, :] / rho[:, None]
+    # consP = 0 is the plain partial derivative (consP = 1 differentiates at constant total
+    # concentration).  Columns of species with third-body efficiency 0 carry the reference's
+    # stale-dqdc quirk (reproduced on purpose, see pelec_b200/mechgen/gen.py) and are skipped.
+    J = orc.rty2jac(rho, T, Y, HP=0)[0][:N, :N]  # [col k][row m] = d wdot_m / d C_k
+    from pelec_b200.mechgen import gen
+    quirk = set()
+    for r in gen.load(mech)["reactions"]:
+        for k, c in r.get("eff", []):
+            if float(c) == -1.0 and k not in r["reactants"] and k not in r["products"]:
+                quirk.add(k)
+    keep = np.array([k for k in range(N) if k not in quirk])
+    Jfd = np.zeros_like(J)
+    h = 1e-4 * 1e-6  # pertMag = 1e-4 mol/m^3
+    for k in range(N):
+        Cp, Cm = C.copy(), C.copy()
+        Cp[0, k] += h
+        Cm[0, k] -= h
+        Jfd[k, :] = (orc.ckwc(T, Cp)[0] - orc.ckwc(T, Cm)[0]) / (2 * h)
+    err = ((J[keep] - Jfd[keep]) ** 2).sum() / (Jfd[keep] ** 2).sum()
+    assert err <= 1e-12, err
+
+
+@pytest.mark.reference
+def test_oracle_vs_reference_library(mech, orc):
+    """Direct check against the unmodified reference (only where oracle/_ref was built)."""
+    if not have_reference(mech):
+        pytest.skip("oracle/_ref not built")
+    ref = Reference(mech)
+    ny = {"LiDryer": 24, "drm19": 8, "dodecane_lu": 2}[mech]
+    st0 = reacteval_states(ref, (1, ny, 1))
+    assert np.array_equal(reacteval_states(orc, (1, ny, 1)).rY, st0.rY)
+    a, b = st0.copy(), st0.copy()
+    ref.react_cvode(b, 2e-6, **CVODE_SETTINGS[2])
+    orc.react_cvode(a, 2e-6, **CVODE_SETTINGS[2])
+    assert np.array_equal(a.rY, b.rY) and np.array_equal(a.T, b.T) and np.array_equal(a.FC, b.FC)
+    if mech != "dodecane_lu":
+        a, b = st0.copy(), st0.copy()
+        ref.react_rk64(b, 2e-6, atol=1e-11)
+        orc.react_rk64(a, 2e-6, atol=1e-11)
+        assert np.array_equal(a.rY, b.rY) and np.array_equal(a.T, b.T) and np.array_equal(a.FC, b.FC)
