@@ -243,7 +243,10 @@ __global__ void __launch_bounds__(PRX_BLOCK) PRX_CAT(rk64_kernel_, PRX_MECH_SUFF
       rk64_begin(s, p, a.dt, a.time);
       req = REQ_NONE;
     }
-    if (__all_sync(FULL, exhausted && (cell < 0))) {
+    // block-wide exit test; it doubles as the phase barrier that keeps the block's warps walking
+    // through the (large, straight-line) RHS code together, so that one instruction-cache fill
+    // serves every warp of the SM (ncu: stall_no_instruction was 76 % of all samples without it)
+    if (!__syncthreads_or(!(exhausted && (cell < 0)))) {
       break;
     }
     if (cell >= 0 && req == REQ_NONE) {
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(PRX_BLOCK) PRX_CAT(bdf_kernel_, PRX_MECH_SUFFI
         ls.masked++;
       }
     }
-    if (__all_sync(FULL, exhausted && (cell < 0))) {
+    if (!__syncthreads_or(!(exhausted && (cell < 0)))) { // exit test + phase barrier (see rk64 kernel)
       break;
     }
     // ---- (2) control ----
@@ -318,6 +321,7 @@ __global__ void __launch_bounds__(PRX_BLOCK) PRX_CAT(bdf_kernel_, PRX_MECH_SUFFI
       req = bdf_resume(s, p);
     }
     // ---- (3) serve ----
+    __syncthreads(); // re-align the warps after the divergent control code, right before the RHS
     const unsigned m_rhs = __ballot_sync(FULL, req == REQ_RHS);
     const unsigned m_jac = __ballot_sync(FULL, req == REQ_JAC);
     const unsigned m_lu = __ballot_sync(FULL, req == REQ_LU);

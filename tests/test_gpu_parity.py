@@ -85,8 +85,13 @@ def test_cvode_matches_golden(mech, i):
     # dense_direct builds J from difference quotients of f with increments ~1.5e-8*|y|: the 1e-10
     # relative rounding noise of the net rates (FMA vs. no FMA) becomes a ~1 % perturbation of J, so two
     # correct runs converge their Newton iterations along different paths and differ at the level of the
-    # Newton tolerance (0.1 * error tolerance) accumulated over the steps -> bar of 100x for that solve type.
-    factor = 10.0 if kw["solve_type"] == "denseAJ_direct" else 100.0
+    # Newton tolerance (0.1 * error tolerance) accumulated over the steps.  MEASURED spread of the reference
+    # algorithm itself: the same C restatement compiled with `-mfma -ffp-contract=fast` differs from the
+    # strict build (= golden, bit for bit) by 237 x (atol + rtol*|y|) on dodecane_lu with this setting and
+    # takes 4723 instead of 4468 RHS calls (tools/fma_spread.py; DESIGN.md "Parity bars").  The GPU always
+    # contracts to FMA, so the dense_direct bar is 1000x; the analytic-Jacobian path (the north-star
+    # path) keeps the 10x bar.
+    factor = 10.0 if kw["solve_type"] == "denseAJ_direct" else 1000.0
     assert_cvode_parity(s.rY, s.T, g["cv%d_rY" % i], g["cv%d_T" % i], kw["atol"], kw["rtol"], factor)
     assert np.array_equal(s.rE, g["cv%d_rE" % i])
     ref_fc = g["cv%d_FC" % i]
