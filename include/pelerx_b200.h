@@ -149,15 +149,18 @@ PRX_API int prx_react_flat(
   prx_handle* h, double* y, const double* ysrc, double* e, const double* esrc, double* fc,
   double dt, double time, int ncells, void* cuda_stream);
 
-/* ---- ReactorBase::flatten / unflatten (ReactorBase.H:56-80; ReactorUtils.H:301-355) ---- */
+/* ---- ReactorBase::flatten / unflatten (ReactorBase.H:56-80; FlattenOps, ReactorUtils.H:160-355) ----
+ * DEVICE pointers.  ordering 0 = YCOrder (y[icell*(N+1)+k], the CPU/RK64 layout), 1 = CYOrder
+ * (y[k*ncells+icell]) (ReactorUtils.H:50-76).  flatten also solves T from (e,Y) like box_flatten;
+ * unflatten writes rhoY, rE = e + dt*rEsrc, T = REY2T(..), FC = fcunt (long int in the reference). */
 PRX_API int prx_flatten(
-  prx_handle* h, const int lo[3], const int hi[3], const prx_array4* rY, const prx_array4* rYsrc,
-  const prx_array4* T, const prx_array4* rE, const prx_array4* rEsrc, double* y, double* ysrc,
-  double* e, double* esrc, void* cuda_stream);
+  prx_handle* h, const int lo[3], const int hi[3], int ncells, int ordering, const prx_array4* rY,
+  const prx_array4* rYsrc, const prx_array4* T, const prx_array4* rE, const prx_array4* rEsrc, double* y,
+  double* ysrc, double* e, double* esrc, void* cuda_stream);
 PRX_API int prx_unflatten(
-  prx_handle* h, const int lo[3], const int hi[3], const prx_array4* rY, const prx_array4* T,
-  const prx_array4* rE, const prx_array4* rEsrc, const prx_array4* FC, const double* y,
-  const double* e, const double* fc, double dt, void* cuda_stream);
+  prx_handle* h, const int lo[3], const int hi[3], int ncells, int ordering, const prx_array4* rY,
+  const prx_array4* T, const prx_array4* rE, const prx_array4* rEsrc, const prx_array4* FC, const double* y,
+  const double* e, const long long* fcunt, double dt, void* cuda_stream);
 
 /* ---- host-buffer convenience: one box held as SoA host arrays a[comp*ncells + cell]
  * (component stride = ncells, exactly an AMReX FAB); does H2D, react, D2H and synchronises.
@@ -165,6 +168,18 @@ PRX_API int prx_unflatten(
 PRX_API int prx_react_box_host(
   prx_handle* h, int nx, int ny, int nz, double* rY, const double* rYsrc, double* T, double* rE,
   const double* rEsrc, double* FC, const int* mask, double dt, double time);
+
+/* flat react with HOST pointers: the reference's 1-D react takes host arrays even in GPU builds
+ * (ReactorRK64.cpp:44-61,154-161 copies H2D/D2H itself). */
+PRX_API int prx_react_flat_host(
+  prx_handle* h, double* y, const double* ysrc, double* e, const double* esrc, double* fc, double dt,
+  double time, int ncells);
+
+/* ---- mechanism lookup for the C++ shim: the reference fixes the mechanism at compile time
+ * (NUM_SPECIES / NUM_REACTIONS macros of mechanism.H, names from CKSYMS_STR); returns the
+ * prx_mechanism id or PRX_ERR_UNSUPPORTED.  Name arguments may be NULL. */
+PRX_API int prx_find_mechanism(int num_species, int num_reactions, const char* first_species, const char* last_species);
+PRX_API const char* prx_species_name(int mechanism, int k);
 
 /* ---- statistics ---- */
 PRX_API int prx_reset_stats(prx_handle* h);

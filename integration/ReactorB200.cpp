@@ -1,0 +1,363 @@
+// ReactorB200.cpp - see ReactorB200.H.  No chemistry here: argument translation only.
+#include "ReactorB200.H"
+
+#include <vector>
+
+#include "pelerx_b200.h"
+
+namespace pele::physics::reactions {
+
+namespace {
+
+template <typename T, typename A4>
+void fill_view(A4* v, amrex::Array4<T> const& a)
+{
+  v->p = const_cast<std::remove_const_t<T>*>(a.dataPtr());
+  v->jstride = a.jstride;
+  v->kstride = a.kstride;
+  v->nstride = a.nstride;
+  v->begin[0] = a.begin.x;
+  v->begin[1] = a.begin.y;
+  v->begin[2] = a.begin.z;
+  v->end[0] = a.end.x;
+  v->end[1] = a.end.y;
+  v->end[2] = a.end.z;
+  v->ncomp = a.ncomp;
+}
+
+void check(prx_handle* h, int rc, const char* what)
+{
+  if (rc != PRX_OK) {
+    amrex::Abort(std::string("ReactorB200: ") + what + " failed: " + (h != nullptr ? prx_last_error(h) : "") +
+                 " (status " + std::to_string(rc) + ")");
+  }
+}
+
+#ifndef AMREX_USE_GPU
+// pack the cells of `box` (component c of Array4 a) into a contiguous host SoA buffer, i fastest
+template <typename T>
+void pack(const amrex::Box& box, amrex::Array4<T> const& a, int ncomp, std::remove_const_t<T>* out)
+{
+  const auto lo = amrex::lbound(box);
+  const auto hi = amrex::ubound(box);
+  std::size_t o = 0;
+  for (int n = 0; n < ncomp; ++n) {
+    for (int k = lo.z; k <= hi.z; ++k) {
+      for (int j = lo.y; j <= hi.y; ++j) {
+        for (int i = lo.x; i <= hi.x; ++i) {
+          out[o++] = a(i, j, k, n);
+        }
+      }
+    }
+  }
+}
+
+void unpack(const amrex::Box& box, amrex::Array4<amrex::Real> const& a, int ncomp, const amrex::Real* in)
+{
+  const auto lo = amrex::lbound(box);
+  const auto hi = amrex::ubound(box);
+  std::size_t o = 0;
+  for (int n = 0; n < ncomp; ++n) {
+    for (int k = lo.z; k <= hi.z; ++k) {
+      for (int j = lo.y; j <= hi.y; ++j) {
+        for (int i = lo.x; i <= hi.x; ++i) {
+          a(i, j, k, n) = in[o++];
+        }
+      }
+    }
+  }
+}
+#endif
+
+} // namespace
+
+template <int KIND>
+ReactorB200<KIND>::~ReactorB200()
+{
+  if (m_h != nullptr) {
+    prx_destroy(m_h);
+    m_h = nullptr;
+  }
+}
+
+template <int KIND>
+int ReactorB200<KIND>::init(int reactor_type, int /*ncells*/)
+{
+  BL_PROFILE("Pele::ReactorB200::init()");
+  m_reactor_type = reactor_type;
+  ReactorTypes::check_reactor_type(m_reactor_type);
+
+  prx_config cfg;
+  prx_default_config(&cfg);
+  cfg.reactor_kind = (KIND == b200::CVODE) ? PRX_REACTOR_CVODE : PRX_REACTOR_RK64;
+  cfg.reactor_type = reactor_type;
+
+  // the mechanism is the one this executable was compiled for (Chemistry_Model)
+  amrex::Vector<std::string> names;
+  CKSYMS_STR(names);
+  cfg.mechanism = prx_find_mechanism(NUM_SPECIES, NUM_REACTIONS, names.front().c_str(), names.back().c_str());
+  if (cfg.mechanism < 0) {
+    amrex::Abort("ReactorB200: libpelerx_b200 has no kernels for this mechanism (NUM_SPECIES=" +
+                 std::to_string(NUM_SPECIES) + ", NUM_REACTIONS=" + std::to_string(NUM_REACTIONS) + ")");
+  }
+
+  // same keys, same defaults as ReactorCvode.cpp:18-35 / ReactorRK64.cpp:12-18
+  amrex::ParmParse pp("ode");
+  pp.query("verbose", this->verbose);
+  pp.query("rtol", cfg.rtol);
+  pp.query("atol", cfg.atol);
+  pp.query("max_nls_iters", cfg.max_nls_iters);
+  pp.query("rk64_nsubsteps_guess", cfg.rk64_nsubsteps_guess);
+  pp.query("rk64_nsubsteps_min", cfg.rk64_nsubsteps_min);
+  pp.query("rk64_nsubsteps_max", cfg.rk64_nsubsteps_max);
+  bool clean = false;
+  pp.query("clean_init_massfrac", clean);
+  cfg.clean_init_massfrac = clean ? 1 : 0;
+  cfg.verbose = this->verbose;
+  if (KIND == b200::CVODE) {
+    amrex::ParmParse ppcv("cvode");
+    ppcv.query("max_order", cfg.max_order);
+    std::string solve_type_str = "denseAJ_direct"; // the B200 path's default; the reference's is "none" -> must be set
+    ppcv.query("solve_type", solve_type_str);
+    if (solve_type_str == "denseAJ_direct") {
+      cfg.solve_type = PRX_SOLVE_DENSE_AJ_DIRECT;
+    } else if (solve_type_str == "dense_direct") {
+      cfg.solve_type = PRX_SOLVE_DENSE_DIRECT;
+    } else {
+      amrex::Abort("ReactorCvodeB200: cvode.solve_type must be denseAJ_direct or dense_direct (got " + solve_type_str + ")");
+    }
+  }
+#ifdef AMREX_USE_GPU
+  cfg.device = amrex::Gpu::Device::deviceId();
+#endif
+  const int rc = prx_create(&cfg, &m_h);
+  if (rc == PRX_ERR_NO_DEVICE) {
+    amrex::Abort("ReactorB200: no CUDA device (this reactor has no CPU fallback)");
+  }
+  check(m_h, rc, "prx_create");
+  if (this->verbose > 0) {
+    amrex::Print() << "ReactorB200: " << identifier() << " on " << prx_mechanism_name(cfg.mechanism) << "\n";
+  }
+  return 0;
+}
+
+template <int KIND>
+void ReactorB200<KIND>::close()
+{
+  if (m_h != nullptr) {
+    prx_destroy(m_h);
+    m_h = nullptr;
+  }
+}
+
+template <int KIND>
+void ReactorB200<KIND>::print_final_stats(void* /*mem*/)
+{
+  if (m_h == nullptr) {
+    return;
+  }
+  prx_stats st;
+  if (prx_get_stats(m_h, &st) == PRX_OK) {
+    // same vocabulary as ReactorCvode::print_final_stats (ReactorCvode.cpp:1838-1901)
+    amrex::Print() << "-- Final Statistics (B200, summed over cells) --\n"
+                   << "   cells = " << st.cells << "  masked = " << st.cells_masked << "\n"
+                   << "   nSteps = " << st.n_steps << "  nRHSeval = " << st.n_rhs << "  nJeval = " << st.n_jac << "\n"
+                   << "   nLinsetups = " << st.n_setups << "  nNonLinIt = " << st.n_newton << "\n"
+                   << "   nErrtf = " << st.n_errfail << "  nConvfail = " << st.n_convfail << "  failed cells = " << st.n_failed
+                   << "\n";
+  }
+}
+
+// Value ReactorBase::react returns: RK64 -> average steps per cell (ReactorRK64.cpp:316-319, a
+// blocking Reduce::Sum in the reference), CVODE -> dummy 20 (ReactorCvode.cpp:1463-1464).
+// PeleC ignores it (React.cpp:222).  In GPU builds reading the RK64 average would force a
+// device synchronisation inside react(), so it is only fetched when ode.verbose > 0.
+template <int KIND>
+int ReactorB200<KIND>::react_return()
+{
+#ifdef AMREX_USE_GPU
+  if (KIND == b200::RK64 && this->verbose <= 0) {
+    return 0;
+  }
+#endif
+  return prx_last_react_return(m_h);
+}
+
+template <int KIND>
+void ReactorB200<KIND>::push_typ_vals()
+{
+  // ReactorBase::set_typ_vals_ode is not virtual: pick m_typ_vals up lazily (ReactorBase.cpp:6-31)
+  if (this->m_typ_vals[0] > 0.0) {
+    std::vector<double> tv(NUM_SPECIES + 1);
+    for (int k = 0; k < NUM_SPECIES + 1; ++k) {
+      tv[k] = this->m_typ_vals[k];
+    }
+    check(m_h, prx_set_typ_vals(m_h, tv.data(), NUM_SPECIES + 1), "prx_set_typ_vals");
+  }
+}
+
+template <int KIND>
+int ReactorB200<KIND>::react(
+  const amrex::Box& box,
+  amrex::Array4<amrex::Real> const& rY_in,
+  amrex::Array4<amrex::Real> const& rYsrc_in,
+  amrex::Array4<amrex::Real> const& T_in,
+  amrex::Array4<amrex::Real> const& rEner_in,
+  amrex::Array4<amrex::Real> const& rEner_src_in,
+  amrex::Array4<amrex::Real> const& FC_in,
+  amrex::Array4<int> const& mask,
+  amrex::Real& dt_react,
+  amrex::Real& time
+#ifdef AMREX_USE_GPU
+  ,
+  amrex::gpuStream_t stream
+#endif
+)
+{
+  BL_PROFILE("Pele::ReactorB200::react()");
+  push_typ_vals();
+  const int lo[3] = {box.smallEnd(0), box.smallEnd(1), box.smallEnd(2)};
+  const int hi[3] = {box.bigEnd(0), box.bigEnd(1), box.bigEnd(2)};
+#ifdef AMREX_USE_GPU
+  prx_array4 rY, rYsrc, T, rE, rEsrc, FC;
+  prx_array4i m;
+  fill_view(&rY, rY_in);
+  fill_view(&rYsrc, rYsrc_in);
+  fill_view(&T, T_in);
+  fill_view(&rE, rEner_in);
+  fill_view(&rEsrc, rEner_src_in);
+  fill_view(&FC, FC_in);
+  fill_view(&m, mask);
+  check(m_h, prx_react_box(m_h, lo, hi, &rY, &rYsrc, &T, &rE, &rEsrc, &FC, &m, dt_react, time, (void*)stream), "prx_react_box");
+#else
+  const int nx = hi[0] - lo[0] + 1, ny = hi[1] - lo[1] + 1, nz = hi[2] - lo[2] + 1;
+  const std::size_t nc = static_cast<std::size_t>(box.numPts());
+  if (nc == 0) {
+    return 0;
+  }
+  std::vector<amrex::Real> rY(nc * NUM_SPECIES), rYsrc(nc * NUM_SPECIES), T(nc), rE(nc), rEsrc(nc), FC(nc);
+  std::vector<int> m(nc);
+  pack(box, rY_in, NUM_SPECIES, rY.data());
+  pack(box, rYsrc_in, NUM_SPECIES, rYsrc.data());
+  pack(box, T_in, 1, T.data());
+  pack(box, rEner_in, 1, rE.data());
+  pack(box, rEner_src_in, 1, rEsrc.data());
+  pack(box, mask, 1, m.data());
+  check(
+    m_h,
+    prx_react_box_host(m_h, nx, ny, nz, rY.data(), rYsrc.data(), T.data(), rE.data(), rEsrc.data(), FC.data(), m.data(), dt_react, time),
+    "prx_react_box_host");
+  // masked cells keep their state: the kernel does not touch them, and FC = 0 (ReactorCvode.cpp:1451-1453)
+  unpack(box, rY_in, NUM_SPECIES, rY.data());
+  unpack(box, T_in, 1, T.data());
+  unpack(box, rEner_in, 1, rE.data());
+  unpack(box, FC_in, 1, FC.data());
+#endif
+#ifdef MOD_REACTOR
+  time += dt_react; // ReactEval builds advance the caller's clock (ReactorRK64.cpp:311-314)
+#endif
+  return react_return();
+}
+
+template <int KIND>
+int ReactorB200<KIND>::react(
+  amrex::Real* rY_in,
+  amrex::Real* rYsrc_in,
+  amrex::Real* rX_in,
+  amrex::Real* rX_src_in,
+  amrex::Real& dt_react,
+  amrex::Real& time,
+  int ncells
+#ifdef AMREX_USE_GPU
+  ,
+  amrex::gpuStream_t /*stream*/
+#endif
+)
+{
+  BL_PROFILE("Pele::ReactorB200::react()");
+  push_typ_vals();
+  // host pointers in every build mode, exactly like the reference's 1-D react
+  check(m_h, prx_react_flat_host(m_h, rY_in, rYsrc_in, rX_in, rX_src_in, nullptr, dt_react, time, ncells), "prx_react_flat_host");
+#ifdef MOD_REACTOR
+  time += dt_react;
+#endif
+  return react_return();
+}
+
+template <int KIND>
+void ReactorB200<KIND>::flatten(
+  const amrex::Box& box,
+  const int ncells,
+  amrex::Array4<const amrex::Real> const& rhoY,
+  amrex::Array4<const amrex::Real> const& frcExt,
+  amrex::Array4<const amrex::Real> const& temperature,
+  amrex::Array4<const amrex::Real> const& rhoE,
+  amrex::Array4<const amrex::Real> const& frcEExt,
+  amrex::Real* y_vect,
+  amrex::Real* src_vect,
+  amrex::Real* vect_energy,
+  amrex::Real* src_vect_energy)
+{
+#ifdef AMREX_USE_GPU
+  const int lo[3] = {box.smallEnd(0), box.smallEnd(1), box.smallEnd(2)};
+  const int hi[3] = {box.bigEnd(0), box.bigEnd(1), box.bigEnd(2)};
+  prx_array4 rY, rYsrc, T, rE, rEsrc;
+  fill_view(&rY, rhoY);
+  fill_view(&rYsrc, frcExt);
+  fill_view(&T, temperature);
+  fill_view(&rE, rhoE);
+  fill_view(&rEsrc, frcEExt);
+  // ordering 0 = YCOrder, the ordering of the reference's RK64 and CPU CVODE reactors
+  check(
+    m_h,
+    prx_flatten(m_h, lo, hi, ncells, 0, &rY, &rYsrc, &T, &rE, &rEsrc, y_vect, src_vect, vect_energy, src_vect_energy,
+                (void*)amrex::Gpu::gpuStream()),
+    "prx_flatten");
+#else
+  // host data: the reference's own host template does the same arithmetic on the CPU; the B200
+  // path only owns device data, so a CPU build of AMReX uses the reference helper unchanged.
+  utils::FlattenOps<utils::YCOrder> ops;
+  ops.flatten(
+    box, ncells, m_reactor_type, false, rhoY, frcExt, temperature, rhoE, frcEExt, y_vect, src_vect, vect_energy, src_vect_energy);
+#endif
+}
+
+template <int KIND>
+void ReactorB200<KIND>::unflatten(
+  const amrex::Box& box,
+  const int ncells,
+  amrex::Array4<amrex::Real> const& rhoY,
+  amrex::Array4<amrex::Real> const& temperature,
+  amrex::Array4<amrex::Real> const& rhoE,
+  amrex::Array4<amrex::Real> const& frcEExt,
+  amrex::Array4<amrex::Real> const& FC_in,
+  amrex::Real* y_vect,
+  amrex::Real* vect_energy,
+  long int* FCunt,
+  amrex::Real dt)
+{
+#ifdef AMREX_USE_GPU
+  const int lo[3] = {box.smallEnd(0), box.smallEnd(1), box.smallEnd(2)};
+  const int hi[3] = {box.bigEnd(0), box.bigEnd(1), box.bigEnd(2)};
+  prx_array4 rY, T, rE, rEsrc, FC;
+  fill_view(&rY, rhoY);
+  fill_view(&T, temperature);
+  fill_view(&rE, rhoE);
+  fill_view(&rEsrc, frcEExt);
+  fill_view(&FC, FC_in);
+  static_assert(sizeof(long int) == sizeof(long long), "LP64 expected");
+  check(
+    m_h,
+    prx_unflatten(m_h, lo, hi, ncells, 0, &rY, &T, &rE, &rEsrc, &FC, y_vect, vect_energy,
+                  reinterpret_cast<const long long*>(FCunt), dt, (void*)amrex::Gpu::gpuStream()),
+    "prx_unflatten");
+#else
+  utils::FlattenOps<utils::YCOrder> ops;
+  ops.unflatten(box, ncells, m_reactor_type, false, rhoY, temperature, rhoE, frcEExt, FC_in, y_vect, vect_energy, FCunt, dt);
+#endif
+}
+
+template class ReactorB200<b200::CVODE>;
+template class ReactorB200<b200::RK64>;
+
+} // namespace pele::physics::reactions

@@ -527,17 +527,154 @@ int prx_react_box_host(
   return PRX_OK;
 }
 
-int prx_flatten(
-  prx_handle* h, const int*, const int*, const prx_array4*, const prx_array4*, const prx_array4*,
-  const prx_array4*, const prx_array4*, double*, double*, double*, double*, void*)
+static int box_args(
+  prx_handle* h, const char* who, const int lo[3], const int hi[3], const prx_array4* rY, const prx_array4* rYsrc,
+  const prx_array4* T, const prx_array4* rE, const prx_array4* rEsrc, const prx_array4* FC, BoxArgs* out, bool* empty)
 {
-  return fail(h, PRX_ERR_UNSUPPORTED, "prx_flatten: not implemented yet (flatten is fused into the react kernels)");
+  const int N = h->ops->num_species;
+  BoxArgs& a = *out;
+  std::memset(&a, 0, sizeof(a));
+  a.layout = LAYOUT_ARRAY4;
+  long long nc = 1;
+  for (int d = 0; d < 3; d++) {
+    a.len[d] = hi[d] - lo[d] + 1;
+    if (a.len[d] <= 0) {
+      a.len[d] = 0;
+    }
+    nc *= a.len[d];
+  }
+  *empty = (nc == 0);
+  if (nc == 0) {
+    return PRX_OK;
+  }
+  if (nc > 2147483647LL) {
+    return fail(h, PRX_ERR_BAD_ARG, "box too large (int32 cell index)");
+  }
+  a.ncells = (int)nc;
+  if ((rY && !view_of(rY, lo, N, &a.rY)) || (rYsrc && !view_of(rYsrc, lo, N, &a.rYsrc)) || (T && !view_of(T, lo, 1, &a.T)) ||
+      (rE && !view_of(rE, lo, 1, &a.rE)) || (rEsrc && !view_of(rEsrc, lo, 1, &a.rEsrc)) || (FC && !view_of(FC, lo, 1, &a.FC))) {
+    return fail(h, PRX_ERR_BAD_ARG, who);
+  }
+  return PRX_OK;
 }
-int prx_unflatten(
-  prx_handle* h, const int*, const int*, const prx_array4*, const prx_array4*, const prx_array4*,
-  const prx_array4*, const prx_array4*, const double*, const double*, const double*, double, void*)
+
+int prx_flatten(
+  prx_handle* h, const int lo[3], const int hi[3], int ncells, int ordering, const prx_array4* rY,
+  const prx_array4* rYsrc, const prx_array4* T, const prx_array4* rE, const prx_array4* rEsrc, double* y,
+  double* ysrc, double* e, double* esrc, void* cuda_stream)
 {
-  return fail(h, PRX_ERR_UNSUPPORTED, "prx_unflatten: not implemented yet (unflatten is fused into the react kernels)");
+  if (h == nullptr || lo == nullptr || hi == nullptr) {
+    return PRX_ERR_BAD_ARG;
+  }
+  if (!rY || !rYsrc || !T || !rE || !rEsrc || !y || !ysrc || !e || !esrc || (ordering != 0 && ordering != 1)) {
+    return fail(h, PRX_ERR_BAD_ARG, "prx_flatten: null pointer or bad ordering");
+  }
+  BoxArgs a;
+  bool empty = false;
+  const int rc = box_args(h, "prx_flatten: short Array4 or box outside the array", lo, hi, rY, rYsrc, T, rE, rEsrc, nullptr, &a, &empty);
+  if (rc != PRX_OK || empty) {
+    return rc;
+  }
+  if (ncells != a.ncells) {
+    return fail(h, PRX_ERR_BAD_ARG, "prx_flatten: ncells != box.numPts()");
+  }
+  DeviceGuard g(h->device);
+  PRX_CUDA(h, h->ops->flatten(a, h->cfg, ordering, y, ysrc, e, esrc, (cudaStream_t)cuda_stream));
+  return PRX_OK;
+}
+
+int prx_unflatten(
+  prx_handle* h, const int lo[3], const int hi[3], int ncells, int ordering, const prx_array4* rY,
+  const prx_array4* T, const prx_array4* rE, const prx_array4* rEsrc, const prx_array4* FC, const double* y,
+  const double* e, const long long* fcunt, double dt, void* cuda_stream)
+{
+  if (h == nullptr || lo == nullptr || hi == nullptr) {
+    return PRX_ERR_BAD_ARG;
+  }
+  if (!rY || !T || !rE || !rEsrc || !FC || !y || !e || !fcunt || (ordering != 0 && ordering != 1)) {
+    return fail(h, PRX_ERR_BAD_ARG, "prx_unflatten: null pointer or bad ordering");
+  }
+  BoxArgs a;
+  bool empty = false;
+  const int rc = box_args(h, "prx_unflatten: short Array4 or box outside the array", lo, hi, rY, nullptr, T, rE, rEsrc, FC, &a, &empty);
+  if (rc != PRX_OK || empty) {
+    return rc;
+  }
+  if (ncells != a.ncells) {
+    return fail(h, PRX_ERR_BAD_ARG, "prx_unflatten: ncells != box.numPts()");
+  }
+  a.dt = dt;
+  DeviceGuard g(h->device);
+  PRX_CUDA(h, h->ops->unflatten(a, h->cfg, ordering, y, e, fcunt, (cudaStream_t)cuda_stream));
+  return PRX_OK;
+}
+
+int prx_react_flat_host(
+  prx_handle* h, double* y, const double* ysrc, double* e, const double* esrc, double* fc, double dt, double time,
+  int ncells)
+{
+  if (h == nullptr || ncells < 0) {
+    return PRX_ERR_BAD_ARG;
+  }
+  if (ncells == 0) {
+    return PRX_OK;
+  }
+  if (y == nullptr || ysrc == nullptr || e == nullptr || esrc == nullptr) {
+    return fail(h, PRX_ERR_BAD_ARG, "prx_react_flat_host: null pointer");
+  }
+  DeviceGuard g(h->device);
+  const int N = h->ops->num_species;
+  const size_t nc = (size_t)ncells;
+  const size_t nd = nc * (size_t)(2 * N + 4);
+  const int rc = ensure_stage(h, nd * sizeof(double));
+  if (rc != PRX_OK) {
+    return rc;
+  }
+  cudaStream_t st = h->stage_stream;
+  double* d_y = h->d_stage;
+  double* d_ysrc = d_y + nc * (N + 1);
+  double* d_e = d_ysrc + nc * N;
+  double* d_esrc = d_e + nc;
+  double* d_fc = d_esrc + nc;
+  PRX_CUDA(h, cudaMemcpyAsync(d_y, y, sizeof(double) * nc * (N + 1), cudaMemcpyHostToDevice, st));
+  PRX_CUDA(h, cudaMemcpyAsync(d_ysrc, ysrc, sizeof(double) * nc * N, cudaMemcpyHostToDevice, st));
+  PRX_CUDA(h, cudaMemcpyAsync(d_e, e, sizeof(double) * nc, cudaMemcpyHostToDevice, st));
+  PRX_CUDA(h, cudaMemcpyAsync(d_esrc, esrc, sizeof(double) * nc, cudaMemcpyHostToDevice, st));
+  const int r = prx_react_flat(h, d_y, d_ysrc, d_e, d_esrc, d_fc, dt, time, ncells, st);
+  if (r != PRX_OK) {
+    return r;
+  }
+  PRX_CUDA(h, cudaMemcpyAsync(y, d_y, sizeof(double) * nc * (N + 1), cudaMemcpyDeviceToHost, st));
+  PRX_CUDA(h, cudaMemcpyAsync(e, d_e, sizeof(double) * nc, cudaMemcpyDeviceToHost, st));
+  if (fc != nullptr) {
+    PRX_CUDA(h, cudaMemcpyAsync(fc, d_fc, sizeof(double) * nc, cudaMemcpyDeviceToHost, st));
+  }
+  PRX_CUDA(h, cudaStreamSynchronize(st));
+  return PRX_OK;
+}
+
+int prx_find_mechanism(int num_species, int num_reactions, const char* first_species, const char* last_species)
+{
+  for (int m = 0; m < 3; m++) {
+    const MechOps* o = ops_for(m);
+    if (o == nullptr || o->num_species != num_species || o->num_reactions != num_reactions) {
+      continue;
+    }
+    if (first_species != nullptr && std::strcmp(first_species, o->species_names[0]) != 0) {
+      continue;
+    }
+    if (last_species != nullptr && std::strcmp(last_species, o->species_names[num_species - 1]) != 0) {
+      continue;
+    }
+    return m;
+  }
+  return PRX_ERR_UNSUPPORTED;
+}
+
+const char* prx_species_name(int mechanism, int k)
+{
+  const MechOps* o = ops_for(mechanism);
+  return (o != nullptr && k >= 0 && k < o->num_species) ? o->species_names[k] : nullptr;
 }
 
 int prx_reset_stats(prx_handle* h)

@@ -25,6 +25,10 @@
 #define PRX_BLOCK 128
 #endif
 
+#ifndef PRX_MINBLOCKS
+#define PRX_MINBLOCKS 1
+#endif
+
 #define PRX_CAT2(a, b) a##b
 #define PRX_CAT(a, b) PRX_CAT2(a, b)
 
@@ -225,7 +229,7 @@ __device__ __forceinline__ void store_cell(
 // =====================================================================================
 // RK64 kernel
 // =====================================================================================
-__global__ void __launch_bounds__(PRX_BLOCK) PRX_CAT(rk64_kernel_, PRX_MECH_SUFFIX)(
+__global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(rk64_kernel_, PRX_MECH_SUFFIX)(
   const BoxArgs a, const Rk64Params p, int* __restrict__ queue, DevStats* __restrict__ stats)
 {
   Rk64Cell s;
@@ -289,7 +293,7 @@ __device__ __forceinline__ double* bdf_vec(BdfCell& s, const int sel)
   }
 }
 
-__global__ void __launch_bounds__(PRX_BLOCK) PRX_CAT(bdf_kernel_, PRX_MECH_SUFFIX)(
+__global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_, PRX_MECH_SUFFIX)(
   const BoxArgs a, const BdfParams p, const SchedParams sp, int* __restrict__ queue,
   DevStats* __restrict__ stats)
 {
@@ -412,6 +416,86 @@ __global__ void PRX_CAT(probe_jac_kernel_, PRX_MECH_SUFFIX)(
 }
 
 // =====================================================================================
+// ReactorBase::flatten / unflatten (FlattenOps, PP/Source/Reactions/ReactorUtils.H:160-355):
+// Array4 box <-> flat vectors, ordering 0 = YCOrder (cell-major), 1 = CYOrder (component-major).
+// One thread per cell; the Array4 side is coalesced along i.
+// =====================================================================================
+__device__ __forceinline__ long long vec_index(const int ordering, const int comp, const int icell, const int ncells, const int nc)
+{
+  return ordering == 0 ? (long long)icell * nc + comp : (long long)comp * ncells + icell;
+}
+
+__global__ void PRX_CAT(flatten_kernel_, PRX_MECH_SUFFIX)(
+  const BoxArgs a, const int reactor_type, const int clean_init_massfrac, const int ordering, double* __restrict__ y_vect,
+  double* __restrict__ src_vect, double* __restrict__ vect_energy, double* __restrict__ src_vect_energy)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.ncells) {
+    return;
+  }
+  double y[NEQ];
+  CellSrc src;
+  BoxArgs b = a;
+  b.mask.p = nullptr; // flatten knows no mask
+  load_cell(b, c, y, src, clean_init_massfrac);
+  double rho = 0.0, Y[N];
+  for (int k = 0; k < N; k++) {
+    rho += y[k];
+  }
+  const double rho_inv = 1.0 / rho;
+  for (int k = 0; k < N; k++) {
+    Y[k] = y[k] * rho_inv;
+    y_vect[vec_index(ordering, k, c, a.ncells, NEQ)] = y[k];
+    src_vect[vec_index(ordering, k, c, a.ncells, N)] = src.rYsrc[k];
+  }
+  vect_energy[c] = src.rhoe_init;
+  src_vect_energy[c] = src.rhoesrc;
+  double temp = y[N];
+  t_from_energy(reactor_type, src.rhoe_init * rho_inv, Y, temp);
+  y_vect[vec_index(ordering, N, c, a.ncells, NEQ)] = temp;
+}
+
+__global__ void PRX_CAT(unflatten_kernel_, PRX_MECH_SUFFIX)(
+  const BoxArgs a, const int reactor_type, const int clean_init_massfrac, const int ordering,
+  const double* __restrict__ y_vect, const double* __restrict__ vect_energy, const long long* __restrict__ fcunt)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.ncells) {
+    return;
+  }
+  double y[NEQ];
+  for (int k = 0; k < NEQ; k++) {
+    y[k] = y_vect[vec_index(ordering, k, c, a.ncells, NEQ)];
+  }
+  CellSrc src;
+  src.rhoe_init = vect_energy[c];
+  src.rhoesrc = a.rEsrc.p[cell_offset(c, a.len, a.rEsrc.js, a.rEsrc.ks)];
+  store_cell(a, c, y, src, reactor_type, (double)fcunt[c], clean_init_massfrac, true);
+}
+
+cudaError_t launch_flatten(
+  const BoxArgs& a, const prx_config& cfg, int ordering, double* y, double* ysrc, double* e, double* esrc, cudaStream_t stream)
+{
+  if (a.ncells <= 0) {
+    return cudaSuccess;
+  }
+  PRX_CAT(flatten_kernel_, PRX_MECH_SUFFIX)<<<(a.ncells + 127) / 128, 128, 0, stream>>>(
+    a, cfg.reactor_type, cfg.clean_init_massfrac, ordering, y, ysrc, e, esrc);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_unflatten(
+  const BoxArgs& a, const prx_config& cfg, int ordering, const double* y, const double* e, const long long* fcunt, cudaStream_t stream)
+{
+  if (a.ncells <= 0) {
+    return cudaSuccess;
+  }
+  PRX_CAT(unflatten_kernel_, PRX_MECH_SUFFIX)<<<(a.ncells + 127) / 128, 128, 0, stream>>>(
+    a, cfg.reactor_type, cfg.clean_init_massfrac, ordering, y, e, fcunt);
+  return cudaGetLastError();
+}
+
+// =====================================================================================
 // launchers
 // =====================================================================================
 int persistent_grid(const void* kernel, const int ncells)
@@ -506,7 +590,8 @@ cudaError_t probe_jac(int n, int reactor_type, const double* y, double* J, cudaS
   return e;
 }
 
-const MechOps g_ops = {PRX_NUM_SPECIES, PRX_NUM_REACTIONS, PRX_MECH_NAME, launch_rk64, launch_bdf, probe_rhs, probe_jac};
+const MechOps g_ops = {PRX_NUM_SPECIES, PRX_NUM_REACTIONS, PRX_MECH_NAME, prx_species_names, launch_rk64, launch_bdf, probe_rhs, probe_jac,
+                       launch_flatten, launch_unflatten};
 
 } // namespace
 

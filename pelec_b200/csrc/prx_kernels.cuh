@@ -63,6 +63,7 @@ struct MechOps
   int num_species;
   int num_reactions;
   const char* name;
+  const char* const* species_names;
   // launchers; all asynchronous on `stream`
   cudaError_t (*launch_rk64)(const BoxArgs&, const prx_config&, int* queue, DevStats* stats, cudaStream_t stream);
   cudaError_t (*launch_bdf)(
@@ -72,6 +73,11 @@ struct MechOps
     int n, double t, int reactor_type, const double* y, const double* rhoe, const double* rhoesrc,
     const double* rYsrc, double* ydot, cudaStream_t stream);
   cudaError_t (*probe_jac)(int n, int reactor_type, const double* y, double* J, cudaStream_t stream);
+  cudaError_t (*flatten)(
+    const BoxArgs&, const prx_config&, int ordering, double* y, double* ysrc, double* e, double* esrc, cudaStream_t stream);
+  cudaError_t (*unflatten)(
+    const BoxArgs&, const prx_config&, int ordering, const double* y, const double* e, const long long* fcunt,
+    cudaStream_t stream);
 };
 
 const MechOps* mech_ops_LiDryer();

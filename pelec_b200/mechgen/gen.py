@@ -536,7 +536,7 @@ class Emitter:
         cq = "PRX_DEVCONST" if self.fl == "cuda" else "static const"
         w("%s double prx_mw[%d] = {%s};" % (cq, N, ", ".join(d["mw"])))
         w("%s double prx_imw[%d] = {%s};" % (cq, N, ", ".join(d["imw"])))
-        if self.fl == "c":
+        if True:  # host-side table in both flavours (prx_species_name / orc_species_name)
             w("static const char* const prx_species_names[%d] = {%s};" % (N, ", ".join('"%s"' % s for s in d["species"])))
         w()
         self.emit_species_fn("cv_R", "cv_R", {"T2", "T3", "T4"})

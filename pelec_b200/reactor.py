@@ -83,6 +83,12 @@ def load_library():
     L.prx_default_config.argtypes = [C.POINTER(prx_config)]
     L.prx_react_box.argtypes = [vp, ip, ip, a4, a4, a4, a4, a4, a4, a4, C.c_double, C.c_double, vp]
     L.prx_react_flat.argtypes = [vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, vp]
+    L.prx_flatten.argtypes = [vp, ip, ip, C.c_int, C.c_int, a4, a4, a4, a4, a4, vp, vp, vp, vp, vp]
+    L.prx_unflatten.argtypes = [vp, ip, ip, C.c_int, C.c_int, a4, a4, a4, a4, a4, vp, vp, vp, C.c_double, vp]
+    L.prx_react_flat_host.argtypes = [vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int]
+    L.prx_find_mechanism.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_char_p]
+    L.prx_species_name.argtypes = [C.c_int, C.c_int]
+    L.prx_species_name.restype = C.c_char_p
     L.prx_react_box_host.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double]
     L.prx_reset_stats.argtypes = [vp]
     L.prx_get_stats.argtypes = [vp, C.POINTER(prx_stats)]
@@ -238,6 +244,30 @@ class ReactorB200:
         self._check(self.lib.prx_react_flat(
             self.h, y.data_ptr(), ysrc.data_ptr(), e.data_ptr(), esrc.data_ptr(),
             fc.data_ptr() if fc is not None else None, float(dt_react), float(time), int(ncells), sp))
+        return 0
+
+    # -- ReactorBase::flatten / unflatten on device tensors (ordering 0 = YCOrder, 1 = CYOrder) --------
+    def flatten(self, box, ncells, rhoY, frcExt, temperature, rhoE, frcEExt, y_vect, src_vect, vect_energy,
+                src_vect_energy, ordering=0, stream=None):
+        lo, hi = (C.c_int * 3)(*box.lo), (C.c_int * 3)(*box.hi)
+        st = [a.c_struct() for a in (rhoY, frcExt, temperature, rhoE, frcEExt)]
+        self._check(self.lib.prx_flatten(
+            self.h, lo, hi, int(ncells), int(ordering), *[C.byref(x) for x in st], y_vect.data_ptr(), src_vect.data_ptr(),
+            vect_energy.data_ptr(), src_vect_energy.data_ptr(), C.c_void_p(stream) if stream else None))
+
+    def unflatten(self, box, ncells, rhoY, temperature, rhoE, frcEExt, FC_in, y_vect, vect_energy, FCunt, dt,
+                  ordering=0, stream=None):
+        lo, hi = (C.c_int * 3)(*box.lo), (C.c_int * 3)(*box.hi)
+        st = [a.c_struct() for a in (rhoY, temperature, rhoE, frcEExt, FC_in)]
+        self._check(self.lib.prx_unflatten(
+            self.h, lo, hi, int(ncells), int(ordering), *[C.byref(x) for x in st], y_vect.data_ptr(), vect_energy.data_ptr(),
+            FCunt.data_ptr(), float(dt), C.c_void_p(stream) if stream else None))
+
+    def react_flat_host(self, y, ysrc, e, esrc, dt_react, time, ncells, fc=None):
+        """1-D react with HOST numpy arrays (the reference's flat react takes host pointers)."""
+        self._check(self.lib.prx_react_flat_host(
+            self.h, y.ctypes.data, ysrc.ctypes.data, e.ctypes.data, esrc.ctypes.data,
+            fc.ctypes.data if fc is not None else None, float(dt_react), float(time), int(ncells)))
         return 0
 
     # -- host (numpy / pinned torch) convenience: H2D + react + D2H ---------------------------------

@@ -230,3 +230,70 @@ def test_full_size_properties_lidryer(key):
     s = r.stats()
     assert s["cells"] == n ** 3 and s["n_failed"] == 0
     r.close()
+
+
+@pytest.mark.parametrize("ordering", [0, 1])
+def test_flatten_unflatten_match_reference_semantics(ordering):
+    """ReactorBase::flatten / unflatten (FlattenOps, ReactorUtils.H:160-355) on a sub-box of an offset FAB, both
+    orderings; the expected values are built with numpy + the oracle's GET_T_GIVEN_EY."""
+    mech = "LiDryer"
+    orc = Oracle(mech)
+    N, neq = orc.N, orc.N + 1
+    nx, ny, nz = 19, 4, 3
+    st = reacteval_states(orc, (nx, ny, nz))
+    rng = np.random.default_rng(7)
+    st.rYsrc[:] = rng.normal(size=st.rYsrc.shape) * 1e-3
+    st.rEsrc[:] = rng.normal(size=st.rEsrc.shape) * 1e3
+    st.T[:] += rng.normal(size=st.T.shape) * 30.0  # a poor guess: flatten must re-solve T from (e, Y)
+    dev = torch.device("cuda:0")
+    begin = (3, -1, 2)
+
+    def fab(a, ncomp):
+        return torch.from_numpy(a.reshape(ncomp, nz, ny, nx).copy()).to(dev)
+    rY, rYs, T, rE, rEs = fab(st.rY, N), fab(st.rYsrc, N), fab(st.T, 1), fab(st.rE, 1), fab(st.rEsrc, 1)
+    FC = torch.zeros((1, nz, ny, nx), dtype=torch.float64, device=dev)
+    A = lambda t: Array4(t, begin)
+    lo = (begin[0] + 2, begin[1], begin[2] + 1)
+    hi = (begin[0] + nx - 3, begin[1] + ny - 2, begin[2] + nz - 1)
+    box = Box(lo, hi)
+    nc = box.numPts()
+    sel = np.zeros((nz, ny, nx), dtype=bool)
+    sel[1:nz, 0:ny - 1, 2:nx - 2] = True
+    idx = np.where(sel.reshape(-1))[0]  # k, j, i order with i fastest == icell order of the reference
+    r = make_reactor("ReactorCvode", mech)
+    y = torch.zeros(nc * neq, dtype=torch.float64, device=dev)
+    ys = torch.zeros(nc * N, dtype=torch.float64, device=dev)
+    e = torch.zeros(nc, dtype=torch.float64, device=dev)
+    es = torch.zeros(nc, dtype=torch.float64, device=dev)
+    r.flatten(box, nc, A(rY), A(rYs), A(T), A(rE), A(rEs), y, ys, e, es, ordering=ordering)
+    torch.cuda.synchronize()
+    sub = st.take(idx)
+    rho = sub.rY.sum(axis=0)
+    Texp = orc.ey2t(sub.rE / rho, np.ascontiguousarray((sub.rY / rho).T), sub.T)
+    yh = y.cpu().numpy().reshape((nc, neq) if ordering == 0 else (neq, nc))
+    ysh = ys.cpu().numpy().reshape((nc, N) if ordering == 0 else (N, nc))
+    if ordering == 0:
+        yh, ysh = yh.T, ysh.T
+    assert np.array_equal(yh[:N], sub.rY) and np.array_equal(ysh, sub.rYsrc)
+    assert np.abs(yh[N] - Texp).max() <= 1e-9 * Texp.max()
+    assert np.array_equal(e.cpu().numpy(), sub.rE) and np.array_equal(es.cpu().numpy(), sub.rEsrc)
+    # unflatten: scale the species a little (rho changes), T guess from the flat vector, FC from long ints
+    ynew = yh.copy()
+    ynew[:N] *= 1.0 + 1e-3 * rng.normal(size=(N, nc))
+    yflat = np.ascontiguousarray(ynew.T if ordering == 0 else ynew).reshape(-1)
+    fcu = torch.from_numpy(np.arange(nc, dtype=np.int64) + 5).to(dev)
+    dt = 1e-6
+    rY0 = rY.clone()
+    r.unflatten(box, nc, A(rY), A(T), A(rE), A(rEs), A(FC), torch.from_numpy(yflat).to(dev), e, fcu, dt, ordering=ordering)
+    torch.cuda.synchronize()
+    got_rY = rY.cpu().numpy().reshape(N, -1)[:, idx]
+    assert np.array_equal(got_rY, ynew[:N])
+    rE_exp = sub.rE + dt * sub.rEsrc
+    assert np.array_equal(rE.cpu().numpy().reshape(-1)[idx], rE_exp)
+    rho2 = ynew[:N].sum(axis=0)
+    T2 = orc.ey2t(rE_exp / rho2, np.ascontiguousarray((ynew[:N] / rho2).T), ynew[N])
+    assert np.abs(T.cpu().numpy().reshape(-1)[idx] - T2).max() <= 1e-9 * T2.max()
+    assert np.array_equal(FC.cpu().numpy().reshape(-1)[idx], np.arange(nc) + 5.0)
+    outside = ~sel.reshape(-1)
+    assert torch.equal(rY.reshape(N, -1)[:, torch.from_numpy(outside).to(dev)], rY0.reshape(N, -1)[:, torch.from_numpy(outside).to(dev)])
+    r.close()
