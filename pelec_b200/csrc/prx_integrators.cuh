@@ -27,7 +27,16 @@
 #ifndef PRX_INTEGRATORS_CUH
 #define PRX_INTEGRATORS_CUH
 
+#include <type_traits>
+
 #include "prx_chem.cuh"
+
+#ifndef PRX_VLOOP
+#define PRX_VLOOP // pragma in front of every per-component vector loop of the BDF control code
+#endif
+#ifndef PRX_MLOOP
+#define PRX_MLOOP // pragma in front of column loops of the dense matrix code
+#endif
 
 namespace prx {
 
@@ -206,14 +215,72 @@ enum BdfFlag {
   CV_TOO_CLOSE = -27
 };
 
-struct BdfCell
+// ---- per-cell storage policies --------------------------------------------------------
+// The integrator addresses its vectors through accessors so that the same state machine runs on
+//  * BdfStoreLocal : plain arrays (host unit tests; legacy thread-local kernels), and
+//  * BdfStoreSmem  : one shared-memory COLUMN per thread - element i of a vector lives at
+//    base[(slot*NEQ + i) * STRIDE] with STRIDE = threads per block, so the 32 lanes of a warp touch
+//    32 consecutive doubles (conflict-free) and the state never leaves the SM.  The zn slots are
+//    sized by cvode.max_order at launch time; the linear-system matrix A optionally sits in the
+//    same column (A_SMEM), savedJ (touched once per setup) stays in thread-local memory (L2).
+template <int STRIDE>
+struct SVecT
 {
-  CellSrc src;
-  // Nordsieck history and work vectors
-  double zn[LMAX][NEQ], ewt[NEQ], acor[NEQ], tempv[NEQ], ftemp[NEQ], y[NEQ], delta[NEQ];
-  // linear system (column-major): A = I - gamma*J factored in place; savedJ = last J
-  double A[NEQ * NEQ], savedJ[NEQ * NEQ];
-  int piv[NEQ];
+  double* p;
+  PRX_MEM double& operator[](const int i) const { return p[i * STRIDE]; }
+};
+
+struct BdfStoreLocal
+{
+  typedef double* Vec;
+  typedef double* Mat;
+  double zn_[LMAX][NEQ], ewt_[NEQ], acor_[NEQ], tempv_[NEQ], ftemp_[NEQ], y_[NEQ], delta_[NEQ];
+  double A_[NEQ * NEQ], savedJ_[NEQ * NEQ];
+  int piv_[NEQ];
+  PRX_MEM Vec zn(const int j) { return zn_[j]; }
+  PRX_MEM Vec ewt() { return ewt_; }
+  PRX_MEM Vec acor() { return acor_; }
+  PRX_MEM Vec tempv() { return tempv_; }
+  PRX_MEM Vec ftemp() { return ftemp_; }
+  PRX_MEM Vec y() { return y_; }
+  PRX_MEM Vec delta() { return delta_; }
+  PRX_MEM Mat A() { return A_; }
+  PRX_MEM double* savedJ() { return savedJ_; }
+  PRX_MEM int* piv() { return piv_; }
+};
+
+template <int STRIDE, bool A_SMEM>
+struct BdfStoreSmem
+{
+  typedef SVecT<STRIDE> Vec;
+  typedef typename std::conditional<A_SMEM, SVecT<STRIDE>, double*>::type Mat;
+  double* base; // this thread's column of the block's dynamic shared memory
+  int nz;       // number of zn slots (qmax + 1)
+  double A_[A_SMEM ? 1 : NEQ * NEQ], savedJ_[NEQ * NEQ];
+  int piv_[NEQ];
+  // vector slots after zn: ewt, acor, tempv, ftemp, y, delta, then N scratch doubles (chemistry), then A
+  static PRX_MEM int doubles_per_thread(const int qmax) { return (qmax + 1 + 6) * NEQ + N + (A_SMEM ? NEQ * NEQ : 0); }
+  PRX_MEM Vec slot(const int s) const { return Vec{base + s * NEQ * STRIDE}; }
+  PRX_MEM Vec zn(const int j) const { return slot(j); }
+  PRX_MEM Vec ewt() const { return slot(nz); }
+  PRX_MEM Vec acor() const { return slot(nz + 1); }
+  PRX_MEM Vec tempv() const { return slot(nz + 2); }
+  PRX_MEM Vec ftemp() const { return slot(nz + 3); }
+  PRX_MEM Vec y() const { return slot(nz + 4); }
+  PRX_MEM Vec delta() const { return slot(nz + 5); }
+  PRX_MEM Vec scratch() const { return Vec{base + (nz + 6) * NEQ * STRIDE}; }
+  PRX_MEM SVecT<STRIDE> A(std::true_type) const { return SVecT<STRIDE>{base + ((nz + 6) * NEQ + N) * STRIDE}; }
+  PRX_MEM double* A(std::false_type) { return A_; }
+  PRX_MEM Mat A() { return A(std::integral_constant<bool, A_SMEM>()); }
+  PRX_MEM double* savedJ() { return savedJ_; }
+  PRX_MEM int* piv() { return piv_; }
+};
+
+template <class Store, class Src = CellSrc>
+struct BdfCellT : public Store
+{
+  typedef typename Store::Vec Vec;
+  Src src;
   // step / order control
   double tn, tout, t0, h, hprime, hscale, eta, etamax, hu;
   double gamma, gammap, gamrat, rl1, crate, delp, acnrm, dsm, saved_t;
@@ -227,15 +294,33 @@ struct BdfCell
   int count1, jcol, lu_info, flag;
   int nst, nfe, nfeDQ, ncfn, netf, nni, nsetups, nstlp, nje, nstlj, nstloc;
   int pc, in_sel, out_sel;
+  PRX_MEM Vec vec(const int sel)
+  {
+    switch (sel) {
+    case V_ZN0:
+      return this->zn(0);
+    case V_ZN1:
+      return this->zn(1);
+    case V_Y:
+      return this->y();
+    case V_TEMPV:
+      return this->tempv();
+    default:
+      return this->ftemp();
+    }
+  }
 };
+typedef BdfCellT<BdfStoreLocal> BdfCell;
 
 constexpr double UROUND = 2.220446049250313e-16;
 constexpr int FIRST_CALL = 6, PREV_CONV_FAIL = 7, PREV_ERR_FAIL = 8;
 constexpr int NLS_CONTINUE = 901, NLS_CONV_RECVR = 902;
 
-PRX_DEV double wrms(const double* x, const double* w)
+template <class VX, class VW>
+PRX_DEV double wrms(VX x, VW w)
 {
   double sum = 0.0;
+  PRX_VLOOP
   for (int i = 0; i < NEQ; i++) {
     const double pr = x[i] * w[i];
     sum += pr * pr;
@@ -243,19 +328,22 @@ PRX_DEV double wrms(const double* x, const double* w)
   return sqrt(sum / NEQ);
 }
 
-PRX_DEV int ewt_set(BdfCell& s, const BdfParams& p, const double* ycur)
+template <class Cell, class VY>
+PRX_DEV int ewt_set(Cell& s, const BdfParams& p, VY ycur)
 {
   int bad = 0;
+  PRX_VLOOP
   for (int i = 0; i < NEQ; i++) {
     const double v = p.rtol * fabs(ycur[i]) + p.atolv[i];
     bad |= !(v > 0.0);
-    s.tempv[i] = v;
+    s.tempv()[i] = v;
   }
   if (bad) {
     return -1;
   }
+  PRX_VLOOP
   for (int i = 0; i < NEQ; i++) {
-    s.ewt[i] = 1.0 / s.tempv[i];
+    s.ewt()[i] = 1.0 / s.tempv()[i];
   }
   return 0;
 }
@@ -271,12 +359,14 @@ PRX_DEV double rpowerI(const double base, const int e)
   return (e < 0) ? 1.0 / prod : prod;
 }
 
-PRX_DEV void bdf_rescale(BdfCell& s)
+template <class Cell>
+PRX_DEV void bdf_rescale(Cell& s)
 {
   double factor = s.eta;
   for (int j = 1; j <= s.q; j++) {
+    PRX_VLOOP
     for (int i = 0; i < NEQ; i++) {
-      s.zn[j][i] *= factor;
+      s.zn(j)[i] *= factor;
     }
     factor *= s.eta;
   }
@@ -284,7 +374,8 @@ PRX_DEV void bdf_rescale(BdfCell& s)
   s.hscale = s.h;
 }
 
-PRX_DEV void bdf_increase_order(BdfCell& s, const int qmax)
+template <class Cell>
+PRX_DEV void bdf_increase_order(Cell& s, const int qmax)
 {
   double alpha0, alpha1, prod, xi, xiold, hsum;
   for (int i = 0; i <= qmax; i++) {
@@ -307,19 +398,22 @@ PRX_DEV void bdf_increase_order(BdfCell& s, const int qmax)
     }
   }
   const double A1 = (-alpha0 - alpha1) / prod;
+  PRX_VLOOP
   for (int i = 0; i < NEQ; i++) {
-    s.zn[s.L][i] = A1 * s.zn[s.indx_acor][i];
+    s.zn(s.L)[i] = A1 * s.zn(s.indx_acor)[i];
   }
   if (s.q > 1) {
     for (int j = 2; j <= s.q; j++) {
+      PRX_VLOOP
       for (int i = 0; i < NEQ; i++) {
-        s.zn[j][i] += s.l[j] * s.zn[s.L][i];
+        s.zn(j)[i] += s.l[j] * s.zn(s.L)[i];
       }
     }
   }
 }
 
-PRX_DEV void bdf_decrease_order(BdfCell& s, const int qmax)
+template <class Cell>
+PRX_DEV void bdf_decrease_order(Cell& s, const int qmax)
 {
   for (int i = 0; i <= qmax; i++) {
     s.l[i] = 0.0;
@@ -335,14 +429,16 @@ PRX_DEV void bdf_decrease_order(BdfCell& s, const int qmax)
   }
   if (s.q > 2) {
     for (int j = 2; j < s.q; j++) {
+      PRX_VLOOP
       for (int i = 0; i < NEQ; i++) {
-        s.zn[j][i] += -s.l[j] * s.zn[s.q][i];
+        s.zn(j)[i] += -s.l[j] * s.zn(s.q)[i];
       }
     }
   }
 }
 
-PRX_DEV void bdf_adjust_order(BdfCell& s, const int deltaq, const int qmax)
+template <class Cell>
+PRX_DEV void bdf_adjust_order(Cell& s, const int deltaq, const int qmax)
 {
   if ((s.q == 2) && (deltaq != 1)) {
     return;
@@ -354,32 +450,37 @@ PRX_DEV void bdf_adjust_order(BdfCell& s, const int deltaq, const int qmax)
   }
 }
 
-PRX_DEV void bdf_predict(BdfCell& s)
+template <class Cell>
+PRX_DEV void bdf_predict(Cell& s)
 {
   s.tn += s.h;
   for (int k = 1; k <= s.q; k++) {
     for (int j = s.q; j >= k; j--) {
+      PRX_VLOOP
       for (int i = 0; i < NEQ; i++) {
-        s.zn[j - 1][i] = s.zn[j - 1][i] + s.zn[j][i];
+        s.zn(j - 1)[i] = s.zn(j - 1)[i] + s.zn(j)[i];
       }
     }
   }
 }
 
-PRX_DEV void bdf_restore(BdfCell& s)
+template <class Cell>
+PRX_DEV void bdf_restore(Cell& s)
 {
   s.tn = s.saved_t;
   for (int k = 1; k <= s.q; k++) {
     for (int j = s.q; j >= k; j--) {
+      PRX_VLOOP
       for (int i = 0; i < NEQ; i++) {
-        s.zn[j - 1][i] = s.zn[j - 1][i] - s.zn[j][i];
+        s.zn(j - 1)[i] = s.zn(j - 1)[i] - s.zn(j)[i];
       }
     }
   }
 }
 
 // cvSet -> cvSetBDF -> cvSetTqBDF (cvode.c:2730-2999)
-PRX_DEV void bdf_set(BdfCell& s)
+template <class Cell>
+PRX_DEV void bdf_set(Cell& s)
 {
   double alpha0, alpha0_hat, xi_inv, xistar_inv, hsum;
   const int q = s.q;
@@ -441,37 +542,41 @@ PRX_DEV void bdf_set(BdfCell& s)
 
 // Dense LU with partial pivoting, same pivot choice and operation order as
 // SUNDlsMat_denseGETRF (column-major, row interchanges applied to the whole row).
-PRX_DEV int dense_getrf(double* a, int* p)
+template <class MA>
+PRX_DEV int dense_getrf(MA a, int* p)
 {
+  PRX_MLOOP
   for (int k = 0; k < NEQ; k++) {
-    double* col_k = a + k * NEQ;
+    const int ck = k * NEQ;
     int l = k;
     for (int i = k + 1; i < NEQ; i++) {
-      if (fabs(col_k[i]) > fabs(col_k[l])) {
+      if (fabs(a[ck + i]) > fabs(a[ck + l])) {
         l = i;
       }
     }
     p[k] = l;
-    if (col_k[l] == 0.0) {
+    if (a[ck + l] == 0.0) {
       return k + 1;
     }
     if (l != k) {
+      PRX_VLOOP
       for (int i = 0; i < NEQ; i++) {
         const double temp = a[i * NEQ + l];
         a[i * NEQ + l] = a[i * NEQ + k];
         a[i * NEQ + k] = temp;
       }
     }
-    const double mult = 1.0 / col_k[k];
+    const double mult = 1.0 / a[ck + k];
     for (int i = k + 1; i < NEQ; i++) {
-      col_k[i] *= mult;
+      a[ck + i] *= mult;
     }
+    PRX_MLOOP
     for (int j = k + 1; j < NEQ; j++) {
-      double* col_j = a + j * NEQ;
-      const double a_kj = col_j[k];
+      const int cj = j * NEQ;
+      const double a_kj = a[cj + k];
       if (a_kj != 0.0) {
         for (int i = k + 1; i < NEQ; i++) {
-          col_j[i] -= a_kj * col_k[i];
+          a[cj + i] -= a_kj * a[ck + i];
         }
       }
     }
@@ -479,7 +584,8 @@ PRX_DEV int dense_getrf(double* a, int* p)
   return 0;
 }
 
-PRX_DEV void dense_getrs(const double* a, const int* p, double* b)
+template <class MA, class VB>
+PRX_DEV void dense_getrs(MA a, const int* p, VB b)
 {
   for (int k = 0; k < NEQ; k++) {
     const int pk = p[k];
@@ -490,24 +596,25 @@ PRX_DEV void dense_getrs(const double* a, const int* p, double* b)
     }
   }
   for (int k = 0; k < NEQ - 1; k++) {
-    const double* col_k = a + k * NEQ;
+    const int ck = k * NEQ;
     const double bk = b[k];
     for (int i = k + 1; i < NEQ; i++) {
-      b[i] -= col_k[i] * bk;
+      b[i] -= a[ck + i] * bk;
     }
   }
   for (int k = NEQ - 1; k > 0; k--) {
-    const double* col_k = a + k * NEQ;
-    b[k] /= col_k[k];
+    const int ck = k * NEQ;
+    b[k] /= a[ck + k];
     const double bk = b[k];
     for (int i = 0; i < k; i++) {
-      b[i] -= col_k[i] * bk;
+      b[i] -= a[ck + i] * bk;
     }
   }
   b[0] /= a[0];
 }
 
-PRX_DEV void bdf_set_eta(BdfCell& s)
+template <class Cell>
+PRX_DEV void bdf_set_eta(Cell& s)
 {
   if ((s.eta > 0.0) && (s.eta < 1.5)) {
     s.eta = 1.0;
@@ -525,7 +632,8 @@ PRX_DEV void bdf_set_eta(BdfCell& s)
 }
 
 // cvPrepareNextStep (+cvComputeEtaqm1/qp1, cvChooseEta), cvode.c:3468-3665
-PRX_DEV void bdf_prepare_next_step(BdfCell& s, const int qmax)
+template <class Cell>
+PRX_DEV void bdf_prepare_next_step(Cell& s, const int qmax)
 {
   if (s.etamax == 1.0) {
     s.qwait = (s.qwait > 2) ? s.qwait : 2;
@@ -544,17 +652,18 @@ PRX_DEV void bdf_prepare_next_step(BdfCell& s, const int qmax)
   s.qwait = 2;
   double etaqm1 = 0.0;
   if (s.q > 1) {
-    const double ddn = wrms(s.zn[s.q], s.ewt) * s.tq[1];
+    const double ddn = wrms(s.zn(s.q), s.ewt()) * s.tq[1];
     etaqm1 = 1.0 / (rpowerR(6.0 * ddn, 1.0 / s.q) + 0.000001);
   }
   double etaqp1 = 0.0;
   if (s.q != qmax) {
     if (s.saved_tq5 != 0.0) {
       const double cquot = (s.tq[5] / s.saved_tq5) * rpowerI(s.h / s.tau[2], s.L);
+      PRX_VLOOP
       for (int i = 0; i < NEQ; i++) {
-        s.tempv[i] = -cquot * s.zn[qmax][i] + s.acor[i];
+        s.tempv()[i] = -cquot * s.zn(qmax)[i] + s.acor()[i];
       }
-      const double dup = wrms(s.tempv, s.ewt) * s.tq[3];
+      const double dup = wrms(s.tempv(), s.ewt()) * s.tq[3];
       etaqp1 = 1.0 / (rpowerR(10.0 * dup, 1.0 / (s.L + 1)) + 0.000001);
     }
   }
@@ -571,36 +680,39 @@ PRX_DEV void bdf_prepare_next_step(BdfCell& s, const int qmax)
   } else {
     s.eta = etaqp1;
     s.qprime = s.q + 1;
+    PRX_VLOOP
     for (int i = 0; i < NEQ; i++) {
-      s.zn[qmax][i] = s.acor[i];
+      s.zn(qmax)[i] = s.acor()[i];
     }
   }
   bdf_set_eta(s);
 }
 
 // Start a cell: zn[0] = (rhoY, T guess); src filled by the caller. (box_flatten, ReactorUtils.H:160-220)
-PRX_DEV void bdf_begin(BdfCell& s, const BdfParams& p, const double dt_react, const double time)
+template <class Cell>
+PRX_DEV void bdf_begin(Cell& s, const BdfParams& p, const double dt_react, const double time)
 {
   if (p.array4_semantics) {
     double rho = 0.0, Y[N];
     for (int k = 0; k < N; k++) {
-      rho += s.zn[0][k];
+      rho += s.zn(0)[k];
     }
     const double rho_inv = 1.0 / rho;
     for (int k = 0; k < N; k++) {
-      Y[k] = s.zn[0][k] * rho_inv;
+      Y[k] = s.zn(0)[k] * rho_inv;
     }
-    double temp = s.zn[0][N];
+    double temp = s.zn(0)[N];
     t_from_energy(p.reactor_type, s.src.rhoe_init * rho_inv, Y, temp);
-    s.zn[0][N] = temp;
+    s.zn(0)[N] = temp;
   }
   s.t0 = time;
   s.tout = time + dt_react;
   s.pc = 0;
 }
 
-// The CVODE state machine.  Returns the next request; on REQ_DONE the answer is in s.y.
-PRX_DEV int bdf_resume(BdfCell& s, const BdfParams& p)
+// The CVODE state machine.  Returns the next request; on REQ_DONE the answer is in s.y().
+template <class Cell>
+PRX_DEV int bdf_resume(Cell& s, const BdfParams& p)
 {
   switch (s.pc) {
   case 0:
@@ -625,10 +737,11 @@ PRX_DEV int bdf_resume(BdfCell& s, const BdfParams& p)
       s.tau[i] = 0.0;
     }
     // ---- first call block of CVode ----
-    if (ewt_set(s, p, s.zn[0]) != 0) {
+    if (ewt_set(s, p, s.zn(0)) != 0) {
       s.flag = CV_ILL_INPUT;
+      PRX_VLOOP
       for (int i = 0; i < NEQ; i++) {
-        s.y[i] = s.zn[0][i];
+        s.y()[i] = s.zn(0)[i];
       }
       break;
     }
@@ -640,17 +753,19 @@ PRX_DEV int bdf_resume(BdfCell& s, const BdfParams& p)
       const double tround = UROUND * fmax(fabs(s.tn), fabs(s.tout));
       if (s.tout == s.tn || tdist < 2.0 * tround) {
         s.flag = CV_TOO_CLOSE;
+        PRX_VLOOP
         for (int i = 0; i < NEQ; i++) {
-          s.y[i] = s.zn[0][i];
+          s.y()[i] = s.zn(0)[i];
         }
         break;
       }
       s.hlb = 100.0 * tround;
       double hub_inv = 0.0;
+      PRX_VLOOP
       for (int i = 0; i < NEQ; i++) {
-        const double t2 = fabs(s.zn[0][i]);
-        const double t1 = 0.1 * t2 + 1.0 / s.ewt[i];
-        const double r = fabs(s.zn[1][i]) / t1;
+        const double t2 = fabs(s.zn(0)[i]);
+        const double t1 = 0.1 * t2 + 1.0 / s.ewt()[i];
+        const double r = fabs(s.zn(1)[i]) / t1;
         hub_inv = (r > hub_inv) ? r : hub_inv;
       }
       s.hub = 0.1 * tdist;
@@ -664,17 +779,19 @@ PRX_DEV int bdf_resume(BdfCell& s, const BdfParams& p)
     } else {
       s.hnew = s.hg;
       for (s.count1 = 1; s.count1 <= 4; s.count1++) {
+        PRX_VLOOP
         for (int i = 0; i < NEQ; i++) {
-          s.y[i] = s.hg * s.zn[1][i] + s.zn[0][i];
+          s.y()[i] = s.hg * s.zn(1)[i] + s.zn(0)[i];
         }
         PRX_YIELD_RHS(2, s.tn + s.hg, V_Y, V_TEMPV);
         s.nfe++;
         {
           const double ihg = 1.0 / s.hg;
+          PRX_VLOOP
           for (int i = 0; i < NEQ; i++) {
-            s.tempv[i] = ihg * (s.tempv[i] - s.zn[1][i]); // N_VLinearSum a == -b: a*(x-y)
+            s.tempv()[i] = ihg * (s.tempv()[i] - s.zn(1)[i]); // N_VLinearSum a == -b: a*(x-y)
           }
-          const double yddnrm = wrms(s.tempv, s.ewt);
+          const double yddnrm = wrms(s.tempv(), s.ewt());
           s.hnew = (yddnrm * s.hub * s.hub > 2.0) ? sqrt(2.0 / yddnrm) : sqrt(s.hg * s.hub);
           if (s.count1 == 4) {
             break;
@@ -701,14 +818,15 @@ PRX_DEV int bdf_resume(BdfCell& s, const BdfParams& p)
     }
     s.hscale = s.h;
     s.hprime = s.h;
+    PRX_VLOOP
     for (int i = 0; i < NEQ; i++) {
-      s.zn[1][i] *= s.h;
+      s.zn(1)[i] *= s.h;
     }
     s.nstloc = 0;
     // ---- main loop of CVode (CV_NORMAL, no tstop) ----
     for (;;) {
       if (s.nst > 0) {
-        if (ewt_set(s, p, s.zn[0]) != 0) {
+        if (ewt_set(s, p, s.zn(0)) != 0) {
           s.flag = CV_ILL_INPUT;
           break;
         }
@@ -717,7 +835,7 @@ PRX_DEV int bdf_resume(BdfCell& s, const BdfParams& p)
         s.flag = CV_TOO_MUCH_WORK;
         break;
       }
-      if (UROUND * wrms(s.zn[0], s.ewt) > 1.0) {
+      if (UROUND * wrms(s.zn(0), s.ewt()) > 1.0) {
         s.flag = CV_TOO_MUCH_ACC;
         break;
       }
@@ -744,20 +862,23 @@ PRX_DEV int bdf_resume(BdfCell& s, const BdfParams& p)
         s.jbad_nls = 0;
         s.nls_jcur = 0;
         s.nls_ok = 0;
+        PRX_VLOOP
         for (int i = 0; i < NEQ; i++) {
-          s.acor[i] = 0.0;
+          s.acor()[i] = 0.0;
         }
         for (;;) { // Newton attempts (second pass: with a fresh Jacobian)
           s.curiter = 0;
+          PRX_VLOOP
           for (int i = 0; i < NEQ; i++) {
-            s.y[i] = s.zn[0][i] + s.acor[i];
+            s.y()[i] = s.zn(0)[i] + s.acor()[i];
           }
           PRX_YIELD_RHS(3, s.tn, V_Y, V_FTEMP);
           s.nfe++;
+          PRX_VLOOP
           for (int i = 0; i < NEQ; i++) {
-            double d = s.rl1 * s.zn[1][i] + s.acor[i];
-            d = -s.gamma * s.ftemp[i] + d;
-            s.delta[i] = d;
+            double d = s.rl1 * s.zn(1)[i] + s.acor()[i];
+            d = -s.gamma * s.ftemp()[i] + d;
+            s.delta()[i] = d;
           }
           s.retval = 0;
           if (s.callSetup) {
@@ -771,45 +892,58 @@ PRX_DEV int bdf_resume(BdfCell& s, const BdfParams& p)
                                ((s.convfail == 1) && (dgamma < 0.2)) || (s.convfail == 2);
               s.jcur = jbad;
             }
-            if (!s.jcur) {
-              for (int i = 0; i < NEQ * NEQ; i++) {
-                s.A[i] = s.savedJ[i];
-              }
-            } else {
+            if (s.jcur) {
               if (p.analytic_jac) {
-                PRX_YIELD(4, REQ_JAC); // kernel fills A with J(tn, y)
+                PRX_YIELD(4, REQ_JAC); // kernel fills savedJ with J(tn, y)
               } else {
                 // cvLsDenseDQJac
                 {
-                  const double fnorm = wrms(s.ftemp, s.ewt);
+                  const double fnorm = wrms(s.ftemp(), s.ewt());
                   s.minInc = (fnorm != 0.0) ? (1000.0 * fabs(s.h) * UROUND * NEQ * fnorm) : 1.0;
                 }
                 for (s.jcol = 0; s.jcol < NEQ; s.jcol++) {
-                  s.yjsaved = s.y[s.jcol];
-                  s.inc = fmax(sqrt(UROUND) * fabs(s.yjsaved), s.minInc / s.ewt[s.jcol]);
-                  s.y[s.jcol] += s.inc;
+                  s.yjsaved = s.y()[s.jcol];
+                  s.inc = fmax(sqrt(UROUND) * fabs(s.yjsaved), s.minInc / s.ewt()[s.jcol]);
+                  s.y()[s.jcol] += s.inc;
                   PRX_YIELD_RHS(5, s.tn, V_Y, V_TEMPV);
                   s.nfeDQ++;
-                  s.y[s.jcol] = s.yjsaved;
+                  s.y()[s.jcol] = s.yjsaved;
                   {
                     const double inc_inv = 1.0 / s.inc;
+                    PRX_VLOOP
                     for (int i = 0; i < NEQ; i++) {
-                      s.A[s.jcol * NEQ + i] = inc_inv * (s.tempv[i] - s.ftemp[i]);
+                      s.savedJ()[s.jcol * NEQ + i] = inc_inv * (s.tempv()[i] - s.ftemp()[i]);
                     }
                   }
                 }
-              }
-              for (int i = 0; i < NEQ * NEQ; i++) {
-                s.savedJ[i] = s.A[i];
+                // the RHS may use delta as scratch (shared-memory kernels): rebuild the Newton residual,
+                // same operands and operations as above, hence the same bits
+                PRX_VLOOP
+                for (int i = 0; i < NEQ; i++) {
+                  double d = s.rl1 * s.zn(1)[i] + s.acor()[i];
+                  d = -s.gamma * s.ftemp()[i] + d;
+                  s.delta()[i] = d;
+                }
               }
               s.nje++;
               s.nstlj = s.nst;
             }
-            for (int j = 0; j < NEQ; j++) {
-              for (int i = 0; i < NEQ; i++) {
-                s.A[j * NEQ + i] *= -s.gamma;
+            // A = I - gamma*J from the saved Jacobian, in one pass (the reference copies savedJ -> A,
+            // scales by -gamma and adds the identity: the same two roundings per entry)
+            {
+              const double mg = -s.gamma;
+              PRX_MLOOP
+              for (int j = 0; j < NEQ; j++) {
+                PRX_VLOOP
+                for (int i = 0; i < NEQ; i++) {
+                  double v = s.savedJ()[j * NEQ + i];
+                  v *= mg;
+                  if (i == j) {
+                    v += 1.0;
+                  }
+                  s.A()[j * NEQ + i] = v;
+                }
               }
-              s.A[j * NEQ + j] += 1.0;
             }
             PRX_YIELD(6, REQ_LU); // kernel factors A in place, sets piv and lu_info
             s.nsetups++;
@@ -825,28 +959,31 @@ PRX_DEV int bdf_resume(BdfCell& s, const BdfParams& p)
           if (s.retval == 0) {
             for (;;) { // Newton iterations
               s.nni++;
+              PRX_VLOOP
               for (int i = 0; i < NEQ; i++) {
-                s.delta[i] = -s.delta[i];
+                s.delta()[i] = -s.delta()[i];
               }
-              dense_getrs(s.A, s.piv, s.delta);
+              dense_getrs(s.A(), s.piv(), s.delta());
               if (s.gamrat != 1.0) {
                 const double sc = 2.0 / (1.0 + s.gamrat);
+                PRX_VLOOP
                 for (int i = 0; i < NEQ; i++) {
-                  s.delta[i] *= sc;
+                  s.delta()[i] *= sc;
                 }
               }
+              PRX_VLOOP
               for (int i = 0; i < NEQ; i++) {
-                s.acor[i] = s.acor[i] + s.delta[i];
+                s.acor()[i] = s.acor()[i] + s.delta()[i];
               }
               {
-                const double del = wrms(s.delta, s.ewt);
+                const double del = wrms(s.delta(), s.ewt());
                 const int m = s.curiter;
                 if (m > 0) {
                   s.crate = fmax(0.3 * s.crate, del / s.delp);
                 }
                 const double dcon = del * fmin(1.0, s.crate) / s.tq[4];
                 if (dcon <= 1.0) {
-                  s.acnrm = (m == 0) ? del : wrms(s.acor, s.ewt);
+                  s.acnrm = (m == 0) ? del : wrms(s.acor(), s.ewt());
                   s.nls_ok = 1;
                   s.retval = 0;
                 } else if ((m >= 1) && (del > 2.0 * s.delp)) {
@@ -864,15 +1001,17 @@ PRX_DEV int bdf_resume(BdfCell& s, const BdfParams& p)
                 s.retval = NLS_CONV_RECVR;
                 break;
               }
+              PRX_VLOOP
               for (int i = 0; i < NEQ; i++) {
-                s.y[i] = s.zn[0][i] + s.acor[i];
+                s.y()[i] = s.zn(0)[i] + s.acor()[i];
               }
               PRX_YIELD_RHS(7, s.tn, V_Y, V_FTEMP);
               s.nfe++;
+              PRX_VLOOP
               for (int i = 0; i < NEQ; i++) {
-                double d = s.rl1 * s.zn[1][i] + s.acor[i];
-                d = -s.gamma * s.ftemp[i] + d;
-                s.delta[i] = d;
+                double d = s.rl1 * s.zn(1)[i] + s.acor()[i];
+                d = -s.gamma * s.ftemp()[i] + d;
+                s.delta()[i] = d;
               }
             }
           }
@@ -882,8 +1021,9 @@ PRX_DEV int bdf_resume(BdfCell& s, const BdfParams& p)
           if ((s.retval > 0) && !s.nls_jcur) {
             s.callSetup = 1;
             s.jbad_nls = 1;
+            PRX_VLOOP
             for (int i = 0; i < NEQ; i++) {
-              s.acor[i] = 0.0;
+              s.acor()[i] = 0.0;
             }
             continue;
           }
@@ -891,8 +1031,9 @@ PRX_DEV int bdf_resume(BdfCell& s, const BdfParams& p)
         }
         if (s.nls_ok) {
           s.jcur = 0;
+          PRX_VLOOP
           for (int i = 0; i < NEQ; i++) {
-            s.y[i] = s.zn[0][i] + s.acor[i];
+            s.y()[i] = s.zn(0)[i] + s.acor()[i];
           }
         } else {
           // ---- cvHandleNFlag: recoverable convergence failure ----
@@ -947,8 +1088,9 @@ PRX_DEV int bdf_resume(BdfCell& s, const BdfParams& p)
         s.qwait = 10;
         PRX_YIELD_RHS(8, s.tn, V_ZN0, V_TEMPV);
         s.nfe++;
+        PRX_VLOOP
         for (int i = 0; i < NEQ; i++) {
-          s.zn[1][i] = s.h * s.tempv[i];
+          s.zn(1)[i] = s.h * s.tempv()[i];
         }
       }
       if (s.flag != CV_SUCCESS) {
@@ -967,14 +1109,16 @@ PRX_DEV int bdf_resume(BdfCell& s, const BdfParams& p)
       s.tau[1] = s.h;
       for (int j = 0; j <= s.q; j++) {
         const double lj = s.l[j];
+        PRX_VLOOP
         for (int i = 0; i < NEQ; i++) {
-          s.zn[j][i] += lj * s.acor[i];
+          s.zn(j)[i] += lj * s.acor()[i];
         }
       }
       s.qwait--;
       if ((s.qwait == 1) && (s.q != p.qmax)) {
+        PRX_VLOOP
         for (int i = 0; i < NEQ; i++) {
-          s.zn[p.qmax][i] = s.acor[i];
+          s.zn(p.qmax)[i] = s.acor()[i];
         }
         s.saved_tq5 = s.tq[5];
         s.indx_acor = p.qmax;
@@ -983,8 +1127,9 @@ PRX_DEV int bdf_resume(BdfCell& s, const BdfParams& p)
       s.etamax = 10.0;
       {
         const double t2 = s.tq[2];
+        PRX_VLOOP
         for (int i = 0; i < NEQ; i++) {
-          s.acor[i] *= t2;
+          s.acor()[i] *= t2;
         }
       }
       s.nstloc++;
@@ -1000,20 +1145,22 @@ PRX_DEV int bdf_resume(BdfCell& s, const BdfParams& p)
           }
           cvals[nvec++] = c;
         }
+        PRX_VLOOP
         for (int i = 0; i < NEQ; i++) {
-          double z = cvals[0] * s.zn[s.q][i];
+          double z = cvals[0] * s.zn(s.q)[i];
           for (int j = 1; j < nvec; j++) {
-            z += cvals[j] * s.zn[s.q - j][i];
+            z += cvals[j] * s.zn(s.q - j)[i];
           }
-          s.y[i] = z;
+          s.y()[i] = z;
         }
         s.pc = 99;
         return REQ_DONE;
       }
     }
     // failure exits: the reference ignores CVode's flag on the CPU path and keeps yout = zn[0]
+    PRX_VLOOP
     for (int i = 0; i < NEQ; i++) {
-      s.y[i] = s.zn[0][i];
+      s.y()[i] = s.zn(0)[i];
     }
     break;
   default:

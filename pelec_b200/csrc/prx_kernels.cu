@@ -281,15 +281,15 @@ __device__ __forceinline__ double* bdf_vec(BdfCell& s, const int sel)
 {
   switch (sel) {
   case V_ZN0:
-    return s.zn[0];
+    return s.zn(0);
   case V_ZN1:
-    return s.zn[1];
+    return s.zn(1);
   case V_Y:
-    return s.y;
+    return s.y();
   case V_TEMPV:
-    return s.tempv;
+    return s.tempv();
   default:
-    return s.ftemp;
+    return s.ftemp();
   }
 }
 
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
     if (got == -2) {
       exhausted = true;
     } else if (got >= 0) {
-      if (load_cell(a, got, s.zn[0], s.src, p.clean_init_massfrac)) {
+      if (load_cell(a, got, s.zn(0), s.src, p.clean_init_massfrac)) {
         cell = got;
         bdf_begin(s, p, a.dt, a.time);
         req = REQ_NONE;
@@ -330,28 +330,27 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
     const unsigned m_jac = __ballot_sync(FULL, req == REQ_JAC);
     const unsigned m_lu = __ballot_sync(FULL, req == REQ_LU);
     if (req == REQ_RHS) {
-      rhs(s.t_eval, p.reactor_type, bdf_vec(s, s.in_sel), bdf_vec(s, s.out_sel), s.src);
+      rhs(s.t_eval, p.reactor_type, s.vec(s.in_sel), s.vec(s.out_sel), s.src);
       req = REQ_NONE;
     }
     if (m_jac && ((__popc(m_jac) >= sp.jac_defer_min_lanes) || (m_rhs == 0))) {
       if (req == REQ_JAC) {
-        double* A = s.A;
-        // savedJ is free here (it is overwritten with the new J right after): use it as scratch
-        jac_analytic(p.reactor_type, s.y, s.savedJ, [A](const int row, const int col, const double v) {
-          A[col * NEQ + row] = v;
+        double* J = s.savedJ(); // raw aJacobian output, scaled in place (each entry is read once, then written)
+        jac_analytic(p.reactor_type, s.y(), J, [J](const int row, const int col, const double v) {
+          J[col * NEQ + row] = v;
         });
         req = REQ_NONE;
       }
     }
     if (m_lu && ((__popc(m_lu) >= sp.lu_defer_min_lanes) || (m_rhs == 0))) {
       if (req == REQ_LU) {
-        s.lu_info = dense_getrf(s.A, s.piv);
+        s.lu_info = dense_getrf(s.A(), s.piv());
         req = REQ_NONE;
       }
     }
     if (req == REQ_DONE) {
       store_cell(
-        a, cell, s.y, s.src, p.reactor_type, double(s.nfe + s.nfeDQ), p.clean_init_massfrac,
+        a, cell, s.y(), s.src, p.reactor_type, double(s.nfe + s.nfeDQ), p.clean_init_massfrac,
         p.array4_semantics != 0);
       ls.cells++;
       ls.steps += s.nst;

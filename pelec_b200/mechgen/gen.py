@@ -503,6 +503,150 @@ class Emitter:
         w("}")
         w()
 
+
+    # ------------------------------------------------------------------ tables
+    def emit_tables(self):
+        """Mechanism as DATA (rolled, table-driven evaluation: prx_tchem.cuh).  Same literals and the same
+        evaluation order as the straight-line code above; each array is emitted in two address spaces -
+        __constant__ (uniform index: every lane of a warp evaluates the same reaction, thread-per-cell
+        kernels) and __device__ global (per-lane index: one warp per cell, lanes over reactions/species) -
+        behind the accessor structs TabC / TabG."""
+        w = self.w
+        d = self.d
+        N = self.N
+        R = d["reactions"]
+        NR = len(R)
+        th = d["thermo"]
+        arrays = []  # (ctype, name, [values as strings])
+
+        def coefs(fname, bases):
+            out = []
+            for k in range(N):
+                t = th[fname][k]
+                for rng in ("lo", "hi"):
+                    terms = t[rng] if t[rng] is not None else t["lo"]
+                    m = {b: c for c, b in terms}
+                    out += [lit(m.get(b, "0.0")) for b in bases]
+            return out
+
+        tm = [t["tmid"] for t in th["cv_R"]]
+        arrays.append(("double", "tmid", [lit(repr(float(x))) if x is not None else "1.0e300" for x in tm]))
+        arrays.append(("double", "cv", coefs("cv_R", ["1", "T", "T2", "T3", "T4"])))
+        arrays.append(("double", "cp", coefs("cp_R", ["1", "T", "T2", "T3", "T4"])))
+        arrays.append(("double", "gb", coefs("gibbs", ["invT", "1", "logT", "T", "T2", "T3", "T4"])))
+        arrays.append(("double", "ei", coefs("speciesInternalEnergy", ["1", "T", "T2", "T3", "T4", "invT"])))
+        arrays.append(("double", "hi", coefs("speciesEnthalpy", ["1", "T", "T2", "T3", "T4", "invT"])))
+        arrays.append(("double", "dc", coefs("dcvpRdT", ["1", "T", "T2", "T3"])))
+        arrays.append(("double", "mw", list(d["mw"])))
+        arrays.append(("double", "imw", list(d["imw"])))
+        # species accumulation order of the mixture sums (ckubms ...): grouped by Tmid like the reference
+        _, groups = self.thermo_groups("cv_R")
+        order = [k for _, ks in groups for k in ks]
+        arrays.append(("unsigned char", "sp_order", [str(k) for k in order]))
+
+        # reactions
+        TYPE = {"elementary": 0, "three_body": 1}
+        meta, fo_of, tb_of = [], [], []
+        A, beta, Ea = [], [], []
+        reac, prod, gidx, gcoef, widx, wcoef = [], [], [], [], [], []
+        eff_ptr, eff_idx, eff_val = [0], [], []
+        lowA, lowb, lowE, fc_a, fc_x, fc_invT, fc_const, fo_flags = [], [], [], [], [], [], [], []
+        for r in R:
+            typ = TYPE.get(r["type"], 2 if r.get("falloff") == "troe" else 3)
+            noexp = r["beta"] is None and r["Ea"] is None
+            assert len(r["reactants"]) <= 3 and len(r["products"]) <= 3 and len(r["wdot"]) <= 5
+            dG = r["dG"] if r["reversible"] else []
+            assert len(dG) <= 6 and -2 <= r["refC"] <= 2
+            m = (typ | (int(bool(r["reversible"])) << 2) | (int(noexp) << 3) | (len(r["reactants"]) << 4)
+                 | (len(r["products"]) << 6) | (len(dG) << 8) | (len(r["wdot"]) << 11) | ((r["refC"] + 2) << 14))
+            meta.append(m)
+            A.append(lit(r["A"]))
+            beta.append(lit(r["beta"]) if r["beta"] is not None else "0.0")
+            Ea.append(lit(r["Ea"]) if r["Ea"] is not None else "0.0")
+            reac += [str(i) for i in r["reactants"]] + ["0"] * (3 - len(r["reactants"]))
+            prod += [str(i) for i in r["products"]] + ["0"] * (3 - len(r["products"]))
+            gidx += [str(k) for c, k in dG] + ["0"] * (6 - len(dG))
+            gcoef += [lit(c) for c, k in dG] + ["0.0"] * (6 - len(dG))
+            widx += [str(k) for k, c in r["wdot"]] + ["0"] * (5 - len(r["wdot"]))
+            wcoef += [lit(c) for k, c in r["wdot"]] + ["0.0"] * (5 - len(r["wdot"]))
+            if typ >= 1:
+                tb_of.append(len(eff_ptr) - 1)
+                for i, c in r["eff"]:
+                    eff_idx.append(str(i))
+                    eff_val.append(lit(c))
+                eff_ptr.append(len(eff_idx))
+            else:
+                tb_of.append(-1)
+            if typ >= 2:
+                fo_of.append(len(lowA))
+                low = r["low"]
+                lowA.append(lit(low["A"]))
+                lowb.append(lit(low["beta"]) if low["beta"] is not None else "0.0")
+                lowE.append(lit(low["Ea"]) if low["Ea"] is not None else "0.0")
+                fc = r.get("fcent") or {"exp_terms": [], "invT_coef": None, "const": None}
+                assert len(fc["exp_terms"]) <= 2
+                et = list(fc["exp_terms"]) + [["0.0", "0.0"]] * (2 - len(fc["exp_terms"]))
+                fc_a += [lit(a) for a, x in et]
+                fc_x += [lit(x) for a, x in et]
+                fc_invT.append(lit(fc["invT_coef"]) if fc["invT_coef"] is not None else "0.0")
+                fc_const.append(lit(fc["const"]) if fc["const"] is not None else "0.0")
+                fo_flags.append(str(len(fc["exp_terms"]) | (int(fc["invT_coef"] is not None) << 2)
+                                    | (int(fc["const"] is not None) << 3)))
+            else:
+                fo_of.append(-1)
+        arrays += [("int", "meta", [str(x) for x in meta]), ("short", "tb_of", [str(x) for x in tb_of]),
+                   ("short", "fo_of", [str(x) for x in fo_of]),
+                   ("double", "A", A), ("double", "beta", beta), ("double", "Ea", Ea),
+                   ("unsigned char", "reac", reac), ("unsigned char", "prod", prod), ("unsigned char", "gidx", gidx),
+                   ("float", "gcoef", gcoef), ("unsigned char", "widx", widx), ("float", "wcoef", wcoef),
+                   ("short", "eff_ptr", [str(x) for x in eff_ptr]), ("unsigned char", "eff_idx", eff_idx or ["0"]),
+                   ("double", "eff_val", eff_val or ["0.0"]),
+                   ("double", "lowA", lowA or ["0.0"]), ("double", "lowb", lowb or ["0.0"]), ("double", "lowE", lowE or ["0.0"]),
+                   ("double", "fc_a", fc_a or ["0.0"]), ("double", "fc_x", fc_x or ["0.0"]),
+                   ("double", "fc_invT", fc_invT or ["0.0"]), ("double", "fc_const", fc_const or ["0.0"]),
+                   ("unsigned char", "fo_flags", fo_flags or ["0"])]
+        # species -> (reaction, coefficient) lists in reaction order (gather form of the wdot accumulation)
+        sp_ptr, sp_r, sp_c = [0], [], []
+        for k in range(N):
+            for ir, r in enumerate(R):
+                for kk, c in r["wdot"]:
+                    if kk == k:
+                        sp_r.append(str(ir))
+                        sp_c.append(lit(c))
+            sp_ptr.append(len(sp_r))
+        arrays += [("short", "sp_ptr", [str(x) for x in sp_ptr]), ("short", "sp_r", sp_r), ("float", "sp_c", sp_c)]
+        for c in gcoef + wcoef + sp_c:  # stoichiometric coefficients must be exact in float
+            import struct
+            assert struct.unpack("f", struct.pack("f", float(c)))[0] == float(c), c
+
+        w("// ---- mechanism tables (see Emitter.emit_tables) ----")
+        w("#define PRX_NUM_FALLOFF %d" % len(lowA))
+        w("#define PRX_REFC_NUM %s" % lit(d["refC_num"]))
+        w("#define PRX_REFC_DEN %s" % d["refC_den"])
+        if self.fl == "cuda":
+            w("#ifdef PRX_HOST_TEST")
+            w("#define PRX_TABC static const")
+            w("#define PRX_TABG static const")
+            w("#define PRX_TABFN static inline")
+            w("#else")
+            w("#define PRX_TABC static __constant__ const")
+            w("#define PRX_TABG static __device__ const")
+            w("#define PRX_TABFN static __device__ __forceinline__")
+            w("#endif")
+        else:
+            w("#define PRX_TABC static const")
+            w("#define PRX_TABG static const")
+        for space, pre in (("PRX_TABC", "tc_"), ("PRX_TABG", "tg_")):
+            for ct, nm, vals in arrays:
+                w("%s %s %s%s[%d] = {%s};" % (space, ct, pre, nm, len(vals), ", ".join(vals)))
+        if self.fl == "cuda":
+            for sname, pre in (("TabC", "tc_"), ("TabG", "tg_")):
+                w("struct %s {" % sname)
+                for ct, nm, vals in arrays:
+                    w("  PRX_TABFN %s %s(const int i) { return %s%s[i]; }" % (ct, nm, pre, nm))
+                w("};")
+        w()
+
     # ------------------------------------------------------------------ whole file
     def emit(self):
         d = self.d
@@ -551,6 +695,7 @@ class Emitter:
         self.emit_mix_fn("ckhbms", "speciesEnthalpy", {"T2", "T3", "T4", "invT"}, True)
         self.emit_production_rate()
         self.emit_ajacobian()
+        self.emit_tables()
         w("#endif")
         return "\n".join(self.L) + "\n"
 

@@ -4,26 +4,17 @@
 #define PRX_HOST_TEST 1
 #include <cstring>
 #include "../../pelec_b200/csrc/prx_integrators.cuh"
+#include "../../pelec_b200/csrc/prx_tchem.cuh"
+
+#include <vector>
 
 using namespace prx;
 
-static double* vsel(BdfCell& s, int sel)
-{
-  switch (sel) {
-  case V_ZN0: return s.zn[0];
-  case V_ZN1: return s.zn[1];
-  case V_Y: return s.y;
-  case V_TEMPV: return s.tempv;
-  default: return s.ftemp;
-  }
-}
-
-extern "C" {
-int hh_num_species() { return N; }
-
-// SoA box arrays a[comp*ncells + cell]; stats[cell*8 + {nst,nfe,nfeDQ,nje,nsetups,nni,ncfn,netf}]
-int hh_react_cvode(
-  int reactor_type, double rtol, double atol, const double* typ_vals, int max_order, int maxcor,
+// One CVODE-per-cell integration of a box on the host.  Cell = BdfCellT<Store>; TAB selects the
+// table-driven RHS (prx_tchem.cuh, tables TB) instead of the generated straight-line one.
+template <class Cell, bool TAB, class TB>
+static int react_cvode_host(
+  Cell& s, int reactor_type, double rtol, double atol, const double* typ_vals, int max_order, int maxcor,
   int analytic_jac, int ncells, double* rY, const double* rYsrc, double* T, double* rE,
   const double* rEsrc, double* FC, const int* mask, double dt, double time, long* stats)
 {
@@ -41,30 +32,47 @@ int hh_react_cvode(
   p.msbj = 100;
   p.clean_init_massfrac = 0;
   p.array4_semantics = 1;
-  static BdfCell s;
+  double scr[2 * N];
   for (int c = 0; c < ncells; c++) {
     if (mask && mask[c] == -1) {
       FC[c] = 0;
       continue;
     }
-    memset(&s, 0, sizeof(s));
     for (int k = 0; k < N; k++) {
-      s.zn[0][k] = rY[k * ncells + c];
+      s.zn(0)[k] = rY[k * ncells + c];
       s.src.rYsrc[k] = rYsrc[k * ncells + c];
     }
-    s.zn[0][N] = T[c];
+    s.zn(0)[N] = T[c];
     s.src.rhoe_init = rE[c];
     s.src.rhoesrc = rEsrc[c];
     bdf_begin(s, p, dt, time);
     for (;;) {
       const int req = bdf_resume(s, p);
       if (req == REQ_RHS) {
-        rhs(s.t_eval, p.reactor_type, vsel(s, s.in_sel), vsel(s, s.out_sel), s.src);
+        if (TAB) {
+          const SrcScalars sc{s.src.rhoe_init, s.src.rhoesrc};
+          const double* src = s.src.rYsrc;
+          rhs_tab<TB>(s.t_eval, p.reactor_type, s.vec(s.in_sel), s.vec(s.out_sel), scr, s.delta(), sc,
+                      [src](int n) { return src[n]; });
+        } else {
+          double yin[NEQ], yout[NEQ];
+          for (int k = 0; k < NEQ; k++) {
+            yin[k] = s.vec(s.in_sel)[k];
+          }
+          rhs(s.t_eval, p.reactor_type, yin, yout, s.src);
+          for (int k = 0; k < NEQ; k++) {
+            s.vec(s.out_sel)[k] = yout[k];
+          }
+        }
       } else if (req == REQ_JAC) {
-        double* A = s.A;
-        jac_analytic(p.reactor_type, s.y, s.savedJ, [A](int row, int col, double v) { A[col * NEQ + row] = v; });
+        double* J = s.savedJ(); // raw aJacobian output scaled in place (each entry is read once, then written)
+        double yy[NEQ];
+        for (int k = 0; k < NEQ; k++) {
+          yy[k] = s.y()[k];
+        }
+        jac_analytic(p.reactor_type, yy, J, [J](int row, int col, double v) { J[col * NEQ + row] = v; });
       } else if (req == REQ_LU) {
-        s.lu_info = dense_getrf(s.A, s.piv);
+        s.lu_info = dense_getrf(s.A(), s.piv());
       } else {
         break;
       }
@@ -72,15 +80,19 @@ int hh_react_cvode(
     // box_unflatten
     double rho = 0.0, Y[N];
     for (int k = 0; k < N; k++) {
-      rY[k * ncells + c] = s.y[k];
-      rho += s.y[k];
+      rY[k * ncells + c] = s.y()[k];
+      rho += s.y()[k];
     }
     for (int k = 0; k < N; k++) {
-      Y[k] = s.y[k] * (1.0 / rho);
+      Y[k] = s.y()[k] * (1.0 / rho);
     }
     rE[c] = s.src.rhoe_init + dt * s.src.rhoesrc;
-    double temp = s.y[N];
-    t_from_energy(reactor_type, rE[c] * (1.0 / rho), Y, temp);
+    double temp = s.y()[N];
+    if (TAB) {
+      t_from_energy_tab<TB>(reactor_type, rE[c] * (1.0 / rho), Y, temp);
+    } else {
+      t_from_energy(reactor_type, rE[c] * (1.0 / rho), Y, temp);
+    }
     T[c] = temp;
     FC[c] = s.nfe + s.nfeDQ;
     if (stats) {
@@ -92,8 +104,89 @@ int hh_react_cvode(
   return 0;
 }
 
-int hh_react_rk64(
-  int reactor_type, double atol, int nsg, int nsmin, int nsmax, int ncells, double* rY,
+extern "C" {
+int hh_num_species() { return N; }
+
+// SoA box arrays a[comp*ncells + cell]; stats[cell*8 + {nst,nfe,nfeDQ,nje,nsetups,nni,ncfn,netf}]
+// variant 0: thread-local arrays + generated RHS; 1: strided "shared-memory column" store with A in the
+// column + table RHS (constant-space tables); 2: strided store, A local + table RHS (global-space tables)
+int hh_react_cvode_variant(
+  int variant, int reactor_type, double rtol, double atol, const double* typ_vals, int max_order, int maxcor,
+  int analytic_jac, int ncells, double* rY, const double* rYsrc, double* T, double* rE,
+  const double* rEsrc, double* FC, const int* mask, double dt, double time, long* stats)
+{
+  if (variant == 0) {
+    static BdfCell s;
+    memset(&s, 0, sizeof(s));
+    return react_cvode_host<BdfCell, false, TabC>(
+      s, reactor_type, rtol, atol, typ_vals, max_order, maxcor, analytic_jac, ncells, rY, rYsrc, T, rE, rEsrc, FC,
+      mask, dt, time, stats);
+  }
+  if (variant == 3) {
+    static BdfCell s;
+    memset(&s, 0, sizeof(s));
+    return react_cvode_host<BdfCell, true, TabC>(
+      s, reactor_type, rtol, atol, typ_vals, max_order, maxcor, analytic_jac, ncells, rY, rYsrc, T, rE, rEsrc, FC,
+      mask, dt, time, stats);
+  }
+  constexpr int STRIDE = 3;
+  if (variant == 1) {
+    typedef BdfCellT<BdfStoreSmem<STRIDE, true>> Cell;
+    static Cell s;
+    memset(&s, 0, sizeof(s));
+    std::vector<double> col((size_t)Cell::doubles_per_thread(max_order) * STRIDE + 8, 0.0);
+    s.base = col.data() + 1;
+    s.nz = max_order + 1;
+    return react_cvode_host<Cell, true, TabC>(
+      s, reactor_type, rtol, atol, typ_vals, max_order, maxcor, analytic_jac, ncells, rY, rYsrc, T, rE, rEsrc, FC,
+      mask, dt, time, stats);
+  }
+  typedef BdfCellT<BdfStoreSmem<STRIDE, false>> Cell;
+  static Cell s;
+  memset(&s, 0, sizeof(s));
+  std::vector<double> col((size_t)Cell::doubles_per_thread(max_order) * STRIDE + 8, 0.0);
+  s.base = col.data() + 2;
+  s.nz = max_order + 1;
+  return react_cvode_host<Cell, true, TabG>(
+    s, reactor_type, rtol, atol, typ_vals, max_order, maxcor, analytic_jac, ncells, rY, rYsrc, T, rE, rEsrc, FC,
+    mask, dt, time, stats);
+}
+
+int hh_react_cvode(
+  int reactor_type, double rtol, double atol, const double* typ_vals, int max_order, int maxcor,
+  int analytic_jac, int ncells, double* rY, const double* rYsrc, double* T, double* rE,
+  const double* rEsrc, double* FC, const int* mask, double dt, double time, long* stats)
+{
+  return hh_react_cvode_variant(
+    0, reactor_type, rtol, atol, typ_vals, max_order, maxcor, analytic_jac, ncells, rY, rYsrc, T, rE, rEsrc, FC, mask,
+    dt, time, stats);
+}
+
+// n states, state-major: generated (tab = 0) or table-driven (tab = 1) RHS
+int hh_rhs(int tab, int n, double t, int reactor_type, const double* y, const double* rhoe, const double* rhoesrc,
+           const double* rYsrc, double* ydot)
+{
+  for (int s = 0; s < n; s++) {
+    CellSrc src;
+    for (int k = 0; k < N; k++) {
+      src.rYsrc[k] = rYsrc[s * N + k];
+    }
+    src.rhoe_init = rhoe[s];
+    src.rhoesrc = rhoesrc[s];
+    if (tab) {
+      double scr[2 * N];
+      const SrcScalars sc{src.rhoe_init, src.rhoesrc};
+      const double* sp = src.rYsrc;
+      rhs_tab<TabG>(t, reactor_type, y + s * NEQ, ydot + s * NEQ, scr, scr + N, sc, [sp](int k) { return sp[k]; });
+    } else {
+      rhs(t, reactor_type, y + s * NEQ, ydot + s * NEQ, src);
+    }
+  }
+  return 0;
+}
+
+int hh_react_rk64_variant(
+  int tab, int reactor_type, double atol, int nsg, int nsmin, int nsmax, int ncells, double* rY,
   const double* rYsrc, double* T, double* rE, const double* rEsrc, double* FC, double dt, double time)
 {
   Rk64Params p{reactor_type, atol, nsg, nsmin, nsmax, 1};
@@ -109,7 +202,14 @@ int hh_react_rk64(
     s.src.rhoesrc = rEsrc[c];
     rk64_begin(s, p, dt, time);
     while (rk64_resume(s, p) == REQ_RHS) {
-      rhs(s.t_eval, p.reactor_type, s.soln, s.ydot, s.src);
+      if (tab) {
+        double scr[2 * N];
+        const SrcScalars sc{s.src.rhoe_init, s.src.rhoesrc};
+        const double* sp = s.src.rYsrc;
+        rhs_tab<TabC>(s.t_eval, p.reactor_type, s.soln, s.ydot, scr, scr + N, sc, [sp](int k) { return sp[k]; });
+      } else {
+        rhs(s.t_eval, p.reactor_type, s.soln, s.ydot, s.src);
+      }
     }
     rE[c] = rk64_finish(s, p);
     for (int k = 0; k < N; k++) {
@@ -119,5 +219,12 @@ int hh_react_rk64(
     FC[c] = s.nsteps;
   }
   return 0;
+}
+
+int hh_react_rk64(
+  int reactor_type, double atol, int nsg, int nsmin, int nsmax, int ncells, double* rY,
+  const double* rYsrc, double* T, double* rE, const double* rEsrc, double* FC, double dt, double time)
+{
+  return hh_react_rk64_variant(0, reactor_type, atol, nsg, nsmin, nsmax, ncells, rY, rYsrc, T, rE, rEsrc, FC, dt, time);
 }
 }

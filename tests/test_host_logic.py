@@ -91,7 +91,7 @@ def harness():
         so = os.path.join(hdir, "libhh_%s.so" % m)
         src = os.path.join(hdir, "harness.cpp")
         deps = [src] + [os.path.join(ROOT, "pelec_b200", "csrc", f) for f in
-                        ("prx_integrators.cuh", "prx_chem.cuh", "gen/mech_%s.cuh" % m)]
+                        ("prx_integrators.cuh", "prx_chem.cuh", "prx_tchem.cuh", "gen/mech_%s.cuh" % m)]
         if not os.path.exists(deps[-1]):
             from pelec_b200.mechgen import gen
             gen.generate_all(ROOT, (m,))
@@ -128,3 +128,48 @@ def test_state_machines_reproduce_oracle(harness, mech):
         hh.hh_react_rk64(C.c_int(1), C.c_double(1e-10), 10, 5, 500, a.ncells, _p(a.rY), _p(a.rYsrc), _p(a.T),
                          _p(a.rE), _p(a.rEsrc), _p(a.FC), C.c_double(dt), C.c_double(0.0))
         assert np.array_equal(a.rY, b.rY) and np.array_equal(a.T, b.T) and np.array_equal(a.FC, b.FC)
+
+
+@pytest.mark.parametrize("mech", MECHS)
+def test_table_driven_chemistry_and_column_store_are_bit_identical(harness, mech):
+    """The table-driven RHS (prx_tchem.cuh: the mechanism as data, both table address spaces) and the
+    strided shared-memory-column store of the integrator state must not change a single bit with respect
+    to the generated straight-line code / thread-local arrays (which the test above pins to the oracle)."""
+    hh = harness[mech]
+    g = golden(mech)
+    dt = float(g["dt"])
+    st = golden_state(g)
+    n, N = st.ncells, st.rY.shape[0]
+    rng = np.random.default_rng(7)
+    # unit level: RHS on the golden states, with external sources and at a later time
+    y = np.concatenate([st.rY.T, st.T[:, None]], axis=1).copy()
+    rYsrc = (rng.standard_normal((n, N)) * 1e-3 * st.rY.T).copy()
+    rEsrc = (rng.standard_normal(n) * 1e-3 * np.abs(st.rE) / dt).copy()
+    outs = []
+    for tab in (0, 1):
+        yd = np.zeros_like(y)
+        hh.hh_rhs(tab, n, C.c_double(0.3 * dt), 1, _p(y), _p(st.rE), _p(rEsrc), _p(rYsrc), _p(yd))
+        outs.append(yd)
+    assert np.array_equal(outs[0], outs[1])
+    assert np.abs(outs[0]).max() > 0
+    # integrator level
+    for kw in CVODE_SETTINGS[:2] if mech == "dodecane_lu" else CVODE_SETTINGS:
+        res = []
+        for variant in (0, 1, 2):
+            a = golden_state(g)
+            a.mask[1::4] = -1
+            hh.hh_react_cvode_variant(variant, 1, C.c_double(kw["rtol"]), C.c_double(kw["atol"]), None, kw["max_order"], 3,
+                                      1 if kw["solve_type"] == "denseAJ_direct" else 0, a.ncells, _p(a.rY), _p(a.rYsrc),
+                                      _p(a.T), _p(a.rE), _p(a.rEsrc), _p(a.FC), a.mask.ctypes.data_as(ip),
+                                      C.c_double(dt), C.c_double(0.0), None)
+            res.append(a)
+        for b in res[1:]:
+            assert np.array_equal(res[0].rY, b.rY) and np.array_equal(res[0].T, b.T) and np.array_equal(res[0].FC, b.FC)
+    if "rk64_rY" in g:
+        res = []
+        for tab in (0, 1):
+            a = golden_state(g)
+            hh.hh_react_rk64_variant(tab, 1, C.c_double(1e-10), 10, 5, 500, a.ncells, _p(a.rY), _p(a.rYsrc), _p(a.T),
+                                     _p(a.rE), _p(a.rEsrc), _p(a.FC), C.c_double(dt), C.c_double(0.0))
+            res.append(a)
+        assert np.array_equal(res[0].rY, res[1].rY) and np.array_equal(res[0].T, res[1].T)
