@@ -302,6 +302,8 @@ int prx_create(const prx_config* cfg, prx_handle** out)
   h->q_next = 0;
   h->sched.jac_defer_min_lanes = env_int("PRX_JAC_DEFER", 1);
   h->sched.lu_defer_min_lanes = env_int("PRX_LU_DEFER", 1);
+  h->sched.bdf_variant = env_int("PRX_BDF_VARIANT", -1);
+  h->sched.max_warps_per_sm = env_int("PRX_MAX_WARPS_PER_SM", 0);
   h->last_ncells = 0;
   h->d_stage = nullptr;
   h->d_stage_bytes = 0;

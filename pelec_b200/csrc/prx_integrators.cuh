@@ -31,11 +31,19 @@
 
 #include "prx_chem.cuh"
 
+// Loop pragmas of the BDF control code.  The device build keeps these loops ROLLED: the control code is
+// cheap arithmetic on shared-memory columns, and unrolling it (NEQ copies of every vector statement)
+// is what pushed the first kernel's hot loop far beyond the instruction cache.
 #ifndef PRX_VLOOP
-#define PRX_VLOOP // pragma in front of every per-component vector loop of the BDF control code
+#ifdef PRX_HOST_TEST
+#define PRX_VLOOP
+#define PRX_MLOOP
+#define PRX_ILOOP
+#else
+#define PRX_VLOOP _Pragma("unroll 1") // per-component vector loops
+#define PRX_MLOOP _Pragma("unroll 1") // column loops of the dense matrix code
+#define PRX_ILOOP _Pragma("unroll 2") // innermost row loops of the dense matrix code
 #endif
-#ifndef PRX_MLOOP
-#define PRX_MLOOP // pragma in front of column loops of the dense matrix code
 #endif
 
 namespace prx {
@@ -549,6 +557,7 @@ PRX_DEV int dense_getrf(MA a, int* p)
   for (int k = 0; k < NEQ; k++) {
     const int ck = k * NEQ;
     int l = k;
+    PRX_VLOOP
     for (int i = k + 1; i < NEQ; i++) {
       if (fabs(a[ck + i]) > fabs(a[ck + l])) {
         l = i;
@@ -567,6 +576,7 @@ PRX_DEV int dense_getrf(MA a, int* p)
       }
     }
     const double mult = 1.0 / a[ck + k];
+    PRX_ILOOP
     for (int i = k + 1; i < NEQ; i++) {
       a[ck + i] *= mult;
     }
@@ -575,6 +585,7 @@ PRX_DEV int dense_getrf(MA a, int* p)
       const int cj = j * NEQ;
       const double a_kj = a[cj + k];
       if (a_kj != 0.0) {
+        PRX_ILOOP
         for (int i = k + 1; i < NEQ; i++) {
           a[cj + i] -= a_kj * a[ck + i];
         }
@@ -587,6 +598,7 @@ PRX_DEV int dense_getrf(MA a, int* p)
 template <class MA, class VB>
 PRX_DEV void dense_getrs(MA a, const int* p, VB b)
 {
+  PRX_VLOOP
   for (int k = 0; k < NEQ; k++) {
     const int pk = p[k];
     if (pk != k) {
@@ -595,17 +607,21 @@ PRX_DEV void dense_getrs(MA a, const int* p, VB b)
       b[pk] = tmp;
     }
   }
+  PRX_MLOOP
   for (int k = 0; k < NEQ - 1; k++) {
     const int ck = k * NEQ;
     const double bk = b[k];
+    PRX_ILOOP
     for (int i = k + 1; i < NEQ; i++) {
       b[i] -= a[ck + i] * bk;
     }
   }
+  PRX_MLOOP
   for (int k = NEQ - 1; k > 0; k--) {
     const int ck = k * NEQ;
     b[k] /= a[ck + k];
     const double bk = b[k];
+    PRX_ILOOP
     for (int i = 0; i < k; i++) {
       b[i] -= a[ck + i] * bk;
     }

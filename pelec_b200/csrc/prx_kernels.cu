@@ -19,6 +19,7 @@
 #include <cstdio>
 
 #include "prx_integrators.cuh"
+#include "prx_tchem.cuh"
 #include "prx_kernels.cuh"
 
 #ifndef PRX_BLOCK
@@ -27,6 +28,10 @@
 
 #ifndef PRX_MINBLOCKS
 #define PRX_MINBLOCKS 1
+#endif
+
+#ifndef PRX_BDF_DEFAULT_VARIANT
+#define PRX_BDF_DEFAULT_VARIANT 0
 #endif
 
 #define PRX_CAT2(a, b) a##b
@@ -370,6 +375,232 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
 }
 
 // =====================================================================================
+// BDF kernel, second generation: integrator state in SHARED-MEMORY COLUMNS + table-driven RHS
+// =====================================================================================
+// What the first kernel's ncu capture showed (profiles/r01a_ncu_bdf_lidryer_64.csv): 478 KB of SASS,
+// 76 % of the stall samples "no instruction", 4.3 KB of thread-local stack per cell spilling to DRAM
+// (28 KB of DRAM traffic per cell against 268 B algorithmic).  Here
+//  * every per-cell vector (zn[0..qmax], ewt, acor, tempv, ftemp, y, delta, a species scratch, and -
+//    template flag - the Newton matrix A) is a column of dynamic shared memory: element i of a vector
+//    sits at base[i*32 + lane], so a warp access is one conflict-free 256-byte row and the state never
+//    leaves the SM;
+//  * the RHS is the rolled, table-driven evaluation of prx_tchem.cuh (mechanism tables in constant
+//    memory: the 32 lanes of a warp evaluate the same reaction, so each table read is a broadcast);
+//    the hot loop (control + RHS + LU + solves) is a few tens of KB of SASS;
+//  * blocks are single warps: no block barrier anywhere, the SM scheduler interleaves independent
+//    warps (as many as the shared memory holds: launch_bdf computes it with the occupancy API);
+//  * the external species source is not copied per cell, it is re-read (coalesced, L2-resident)
+//    through SrcRef at every RHS.
+#define PRX_HAVE_BDF2 (PRX_NUM_SPECIES <= 32) // one cell per thread stops making sense beyond that
+#if PRX_HAVE_BDF2
+struct SrcRef
+{
+  double rhoe_init, rhoesrc;
+  const double* p; // rYsrc of this cell, component k at p[k*stride]
+  long long stride;
+};
+
+extern __shared__ double prx_dyn_smem[];
+
+template <bool A_SMEM>
+__global__ void __launch_bounds__(32) PRX_CAT(bdf2_kernel_, PRX_MECH_SUFFIX)(
+  const BoxArgs a, const BdfParams p, const SchedParams sp, int* __restrict__ queue, DevStats* __restrict__ stats)
+{
+  typedef BdfCellT<BdfStoreSmem<32, A_SMEM>, SrcRef> Cell;
+  Cell s;
+  s.base = prx_dyn_smem + threadIdx.x;
+  s.nz = p.qmax + 1;
+  int cell = -1;
+  bool exhausted = false;
+  int req = REQ_NONE;
+  LaneStats ls = {};
+  BdfParams pc = p;
+  pc.array4_semantics = 0; // the initial T solve is done here with the table-driven Newton loop
+  for (;;) {
+    // ---- (1) refill ----
+    const int got = fetch_cell((cell < 0) && !exhausted, queue, a.ncells);
+    if (got == -2) {
+      exhausted = true;
+    } else if (got >= 0) {
+      double y0[NEQ];
+      CellSrc cs;
+      if (load_cell(a, got, y0, cs, p.clean_init_massfrac)) {
+        cell = got;
+        s.src.rhoe_init = cs.rhoe_init;
+        s.src.rhoesrc = cs.rhoesrc;
+        if (a.layout == LAYOUT_ARRAY4) {
+          s.src.p = a.rYsrc.p + cell_offset(got, a.len, a.rYsrc.js, a.rYsrc.ks);
+          s.src.stride = a.rYsrc.ns;
+        } else {
+          s.src.p = a.ysrc + (long long)got * N;
+          s.src.stride = 1;
+        }
+        double rho = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+          s.zn(0)[k] = y0[k];
+          rho += y0[k];
+        }
+        double temp = y0[N];
+        if (p.array4_semantics) { // box_flatten re-solves T from (e, Y) (ReactorUtils.H:206-219)
+          const double rho_inv = 1.0 / rho;
+#pragma unroll
+          for (int k = 0; k < N; k++) {
+            s.scratch()[k] = y0[k] * rho_inv;
+          }
+          t_from_energy_tab<TabC>(p.reactor_type, cs.rhoe_init * rho_inv, s.scratch(), temp);
+        }
+        s.zn(0)[N] = temp;
+        bdf_begin(s, pc, a.dt, a.time);
+        req = REQ_NONE;
+      } else {
+        store_masked(a, got);
+        ls.masked++;
+      }
+    }
+    if (!__any_sync(FULL, !(exhausted && (cell < 0)))) {
+      break;
+    }
+    // ---- (2) control ----
+    if (cell >= 0 && req == REQ_NONE) {
+      req = bdf_resume(s, pc);
+    }
+    __syncwarp();
+    // ---- (3) serve ----
+    const unsigned m_rhs = __ballot_sync(FULL, req == REQ_RHS);
+    const unsigned m_jac = __ballot_sync(FULL, req == REQ_JAC);
+    const unsigned m_lu = __ballot_sync(FULL, req == REQ_LU);
+    if (req == REQ_RHS) {
+      const SrcScalars sc{s.src.rhoe_init, s.src.rhoesrc};
+      const double* sp_p = s.src.p;
+      const long long sp_s = s.src.stride;
+      rhs_tab<TabC>(
+        s.t_eval, p.reactor_type, s.vec(s.in_sel), s.vec(s.out_sel), s.scratch(), s.delta(), sc,
+        [sp_p, sp_s](const int n) { return __ldg(sp_p + n * sp_s); });
+      req = REQ_NONE;
+    }
+    __syncwarp();
+    if (m_jac && ((__popc(m_jac) >= sp.jac_defer_min_lanes) || (m_rhs == 0))) {
+      if (req == REQ_JAC) {
+        double yy[NEQ];
+#pragma unroll
+        for (int k = 0; k < NEQ; k++) {
+          yy[k] = s.y()[k];
+        }
+        double* J = s.savedJ();
+        jac_analytic(p.reactor_type, yy, J, [J](const int row, const int col, const double v) { J[col * NEQ + row] = v; });
+        req = REQ_NONE;
+      }
+      __syncwarp();
+    }
+    if (m_lu && ((__popc(m_lu) >= sp.lu_defer_min_lanes) || (m_rhs == 0))) {
+      if (req == REQ_LU) {
+        s.lu_info = dense_getrf(s.A(), s.piv());
+        req = REQ_NONE;
+      }
+      __syncwarp();
+    }
+    if (req == REQ_DONE) {
+      // box_unflatten (ReactorUtils.H:222-291)
+      const double rhoe_out = s.src.rhoe_init + a.dt * s.src.rhoesrc;
+      const double fc = double(s.nfe + s.nfeDQ);
+      if (a.layout == LAYOUT_ARRAY4) {
+        const long long o = cell_offset(cell, a.len, a.rY.js, a.rY.ks);
+        double rho = 0.0;
+        if (p.clean_init_massfrac) {
+          double rho_old = 0.0, rho_oldclipped = 0.0;
+          for (int k = 0; k < N; k++) {
+            rho_old += a.rY.p[o + k * a.rY.ns];
+          }
+          for (int k = 0; k < N; k++) {
+            rho_oldclipped += fmin(fmax(0.0, a.rY.p[o + k * a.rY.ns]), rho_old);
+          }
+          for (int k = 0; k < N; k++) {
+            const double yold = a.rY.p[o + k * a.rY.ns];
+            const double clipped = fmin(fmax(0.0, yold), rho_old);
+            s.y()[k] = yold + (s.y()[k] - clipped) * rho_old / rho_oldclipped;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+          const double v = s.y()[k];
+          a.rY.p[o + k * a.rY.ns] = v;
+          rho += v;
+        }
+        const double rho_inv = 1.0 / rho;
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+          s.scratch()[k] = s.y()[k] * rho_inv;
+        }
+        double temp = s.y()[N];
+        t_from_energy_tab<TabC>(p.reactor_type, rhoe_out * rho_inv, s.scratch(), temp);
+        a.rE.p[cell_offset(cell, a.len, a.rE.js, a.rE.ks)] = rhoe_out;
+        a.T.p[cell_offset(cell, a.len, a.T.js, a.T.ks)] = temp;
+        a.FC.p[cell_offset(cell, a.len, a.FC.js, a.FC.ks)] = fc;
+      } else {
+#pragma unroll
+        for (int k = 0; k < NEQ; k++) {
+          a.y[(long long)cell * NEQ + k] = s.y()[k];
+        }
+        a.e[cell] = rhoe_out;
+        if (a.fc != nullptr) {
+          a.fc[cell] = fc;
+        }
+      }
+      ls.cells++;
+      ls.steps += s.nst;
+      ls.rhs += s.nfe + s.nfeDQ;
+      ls.jac += s.nje;
+      ls.setups += s.nsetups;
+      ls.newton += s.nni;
+      ls.errfail += s.netf;
+      ls.convfail += s.ncfn;
+      ls.failed += (s.flag != CV_SUCCESS);
+      ls.maxsteps = (unsigned long long)s.nst > ls.maxsteps ? s.nst : ls.maxsteps;
+      cell = -1;
+      req = REQ_NONE;
+    }
+  }
+  flush_stats(ls, stats);
+}
+
+template <bool A_SMEM>
+cudaError_t launch_bdf2(const BoxArgs& a, const BdfParams& p, const SchedParams& sp, int* queue, DevStats* stats, cudaStream_t stream)
+{
+  typedef BdfStoreSmem<32, A_SMEM> Store;
+  auto kern = PRX_CAT(bdf2_kernel_, PRX_MECH_SUFFIX)<A_SMEM>;
+  const size_t smem = sizeof(double) * 32 * (size_t)Store::doubles_per_thread(p.qmax);
+  int dev = 0, sms = 148, per_sm = 0, max_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (smem > (size_t)max_optin) {
+    return cudaErrorInvalidConfiguration;
+  }
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    return e;
+  }
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem) != cudaSuccess || per_sm < 1) {
+    return cudaErrorInvalidConfiguration;
+  }
+  if (sp.max_warps_per_sm > 0 && per_sm > sp.max_warps_per_sm) {
+    per_sm = sp.max_warps_per_sm;
+  }
+  long long grid = (long long)sms * per_sm; // persistent: one full wave, a multiple of the SM count
+  const long long needed = ((long long)a.ncells + 31) / 32;
+  grid = needed < grid ? needed : grid;
+  e = cudaMemsetAsync(queue, 0, sizeof(int), stream);
+  if (e != cudaSuccess) {
+    return e;
+  }
+  kern<<<(int)grid, 32, smem, stream>>>(a, p, sp, queue, stats);
+  return cudaGetLastError();
+}
+#endif // PRX_HAVE_BDF2
+
+// =====================================================================================
 // probes (parity tests of the device thermo-chemistry)
 // =====================================================================================
 __global__ void PRX_CAT(probe_rhs_kernel_, PRX_MECH_SUFFIX)(
@@ -556,6 +787,20 @@ cudaError_t launch_bdf(
   p.msbj = 100;
   p.clean_init_massfrac = cfg.clean_init_massfrac;
   p.array4_semantics = (a.layout == LAYOUT_ARRAY4);
+  // kernel generation: 1 = shared-memory columns incl. the Newton matrix, 2 = columns, matrix thread-local,
+  // 0 = first generation (thread-local state, straight-line chemistry); default per mechanism
+  int variant = sp.bdf_variant;
+  if (variant < 0) {
+    variant = PRX_BDF_DEFAULT_VARIANT;
+  }
+#if PRX_HAVE_BDF2
+  if (variant == 1) {
+    return launch_bdf2<true>(a, p, sp, queue, stats, stream);
+  }
+  if (variant == 2) {
+    return launch_bdf2<false>(a, p, sp, queue, stats, stream);
+  }
+#endif
   auto kern = PRX_CAT(bdf_kernel_, PRX_MECH_SUFFIX);
   const int grid = persistent_grid((const void*)kern, a.ncells);
   cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(int), stream);

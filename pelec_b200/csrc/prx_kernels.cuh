@@ -56,6 +56,8 @@ struct SchedParams
 {
   int jac_defer_min_lanes; // serve REQ_JAC only when >= this many lanes ask (or nobody has RHS work)
   int lu_defer_min_lanes;
+  int bdf_variant;      // BDF kernel generation (-1: the mechanism's default), see launch_bdf
+  int max_warps_per_sm; // cap on resident warps of the shared-memory-column kernels (0: occupancy limit)
 };
 
 struct MechOps

@@ -24,6 +24,11 @@
 #ifndef PRX_SP_UNROLL
 #define PRX_SP_UNROLL _Pragma("unroll")
 #endif
+#ifdef PRX_HOST_TEST
+#define PRX_ROLLED
+#else
+#define PRX_ROLLED _Pragma("unroll 1")
+#endif
 #ifndef PRX_RX_UNROLL
 #define PRX_RX_UNROLL _Pragma("unroll 2")
 #endif
@@ -110,7 +115,7 @@ PRX_DEV double sp_dcvpRdT(const int k, const TPow& p)
 // CKUBMS / CKHBMS (ETYPE 1 / 2) and CKCVBS / CKCPBS: mass-fraction weighted mixture sums, species
 // accumulated in the reference's order (grouped by Tmid).
 template <class TB, int ETYPE, class YV>
-PRX_DEV double mix_energy(const double T, YV Y)
+PRX_DEV_NOINLINE double mix_energy(const double T, YV Y)
 {
   const TPow p = tpow_poly(T);
   double result = 0.0;
@@ -124,7 +129,7 @@ PRX_DEV double mix_energy(const double T, YV Y)
   return result * RT;
 }
 template <class TB, int ETYPE, class YV>
-PRX_DEV double mix_cvp(const double T, YV Y)
+PRX_DEV_NOINLINE double mix_cvp(const double T, YV Y)
 {
   const TPow p = tpow_poly(T);
   double result = 0.0;
@@ -139,7 +144,7 @@ PRX_DEV double mix_cvp(const double T, YV Y)
 
 // GET_T_GIVEN_EY / GET_T_GIVEN_HY - same control flow as t_from_energy (prx_chem.cuh)
 template <class TB, int ETYPE, class YV>
-PRX_DEV_NOINLINE void t_from_energy_tab_impl(const double e, YV y, double& t)
+PRX_DEV void t_from_energy_tab_impl(const double e, YV y, double& t)
 {
   const double tmin = PRX_TMIN, tmax = PRX_TMAX;
   const double emin = mix_energy<TB, ETYPE>(tmin, y);
@@ -156,6 +161,7 @@ PRX_DEV_NOINLINE void t_from_energy_tab_impl(const double e, YV y, double& t)
   if (t1 < tmin || t1 > tmax) {
     t1 = tmin + (tmax - tmin) / (emax - emin) * (e - emin);
   }
+  PRX_ROLLED
   for (int i = 0; i < 200; ++i) {
     const double e1 = mix_energy<TB, ETYPE>(t1, y);
     const double cv = mix_cvp<TB, ETYPE>(t1, y);
