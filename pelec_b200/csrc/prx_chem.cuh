@@ -22,12 +22,14 @@
 #define PRX_DEV static inline
 #define PRX_DEV_NOINLINE static
 #define PRX_MEM inline
+#define PRX_HD inline
 #else
 #define PRX_DEVFN __device__ __forceinline__
 #define PRX_DEVCONST static __constant__ const
 #define PRX_DEV __device__ __forceinline__
 #define PRX_DEV_NOINLINE __device__ __noinline__
 #define PRX_MEM __device__ __forceinline__
+#define PRX_HD __host__ __device__ __forceinline__
 #endif
 
 #include PRX_MECH_HEADER

@@ -267,7 +267,7 @@ struct BdfStoreSmem
   double A_[A_SMEM ? 1 : NEQ * NEQ], savedJ_[NEQ * NEQ];
   int piv_[NEQ];
   // vector slots after zn: ewt, acor, tempv, ftemp, y, delta, then N scratch doubles (chemistry), then A
-  static PRX_MEM int doubles_per_thread(const int qmax) { return (qmax + 1 + 6) * NEQ + N + (A_SMEM ? NEQ * NEQ : 0); }
+  static PRX_HD int doubles_per_thread(const int qmax) { return (qmax + 1 + 6) * NEQ + N + (A_SMEM ? NEQ * NEQ : 0); }
   PRX_MEM Vec slot(const int s) const { return Vec{base + s * NEQ * STRIDE}; }
   PRX_MEM Vec zn(const int j) const { return slot(j); }
   PRX_MEM Vec ewt() const { return slot(nz); }

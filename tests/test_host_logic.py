@@ -37,6 +37,10 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.check_output(["nm", "-D", "--defined-only", LIB]).decode()
     exported = [l.split()[-1] for l in out.splitlines() if " T " in l]
     assert all(e.startswith("prx_") for e in exported), exported
+    # nvcc compiles a host call of a __device__-only function (reachable through a template) into a silent
+    # exit(1): the library must not import exit at all
+    und = subprocess.check_output(["nm", "-D", "--undefined-only", LIB]).decode()
+    assert not re.search(r"\bU exit\b", und), "host code calls a __device__ function (nvcc emitted exit(1))"
 
 
 def test_metadata_and_argument_checks_without_device():
