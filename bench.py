@@ -311,7 +311,7 @@ def run_b200(a):
                 "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
                 "frac": achieved / peak.value if peak.value > 0 else None, "traffic": None,
                 "peak_source": "measured in this run: register-resident DFMA chains (prx_measure_fp64_peak)",
-                "kernel": "bdf_kernel_%s" % a.mech if a.reactor == "ReactorCvode" else "rk64_kernel_%s" % a.mech,
+                "kernel": r.kernel_name(),
                 "kernel_ms": kms, "flops_per_launch": flops_per_launch,
                 "flop_model": {k: oc[k] for k in ("F_rhs", "T_rhs", "F_jac", "T_jac", "F_lu", "F_slv", "F_vec")},
                 "hbm": {"algorithmic_GBps": hbm_alg, "peak_GBps": hbm_peak, "frac": hbm_alg / hbm_peak,

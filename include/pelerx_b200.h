@@ -185,6 +185,7 @@ PRX_API const char* prx_species_name(int mechanism, int k);
 PRX_API int prx_reset_stats(prx_handle* h);
 PRX_API int prx_get_stats(prx_handle* h, prx_stats* out); /* synchronises the handle's streams */
 PRX_API int prx_last_react_return(prx_handle* h);        /* value ReactorBase::react would return */
+PRX_API const char* prx_kernel_name(const prx_handle* h); /* name of the integrator kernel this handle launches */
 
 /* ---- device probes used by the parity tests (n states, state-major host arrays) ---- */
 PRX_API int prx_probe_rhs_host(

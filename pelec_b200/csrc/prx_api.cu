@@ -714,6 +714,11 @@ int prx_get_stats(prx_handle* h, prx_stats* out)
   return PRX_OK;
 }
 
+const char* prx_kernel_name(const prx_handle* h)
+{
+  return h ? h->ops->kernel_name(h->cfg.reactor_kind, h->sched) : "";
+}
+
 int prx_last_react_return(prx_handle* h)
 {
   if (h == nullptr) {

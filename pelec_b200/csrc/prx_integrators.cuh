@@ -46,7 +46,25 @@
 #endif
 #endif
 
+// Per-component vector loop of the integrator: the storage policy decides which elements THIS thread owns.
+//   serial policies (one thread per cell): all of them, i = 0, 1, ..., NEQ-1;
+//   cooperative policy (G lanes per cell): i = lane_in_group, +G, ... - the loop body is one or two
+//   SIMD statements and reductions go through s.gsum / s.gmax / s.gor (warp shuffles).
+#define PRX_VEC_FOR(i) PRX_VLOOP for (int i = s.vbegin(); i < NEQ; i += s.vstep())
+
 namespace prx {
+
+// what a one-thread-per-cell storage policy answers to the cooperative hooks
+struct SerialOwner
+{
+  PRX_MEM int vbegin() const { return 0; }
+  PRX_MEM int vstep() const { return 1; }
+  PRX_MEM bool owns(const int) const { return true; }
+  PRX_MEM double gsum(const double x) const { return x; }
+  PRX_MEM double gmax(const double x) const { return x; }
+  PRX_MEM int gor(const int x) const { return x; }
+  PRX_MEM void sync() const {}
+};
 
 enum Request { REQ_NONE = 0, REQ_RHS = 1, REQ_JAC = 2, REQ_LU = 3, REQ_DONE = 4 };
 
@@ -238,7 +256,7 @@ struct SVecT
   PRX_MEM double& operator[](const int i) const { return p[i * STRIDE]; }
 };
 
-struct BdfStoreLocal
+struct BdfStoreLocal : public SerialOwner
 {
   typedef double* Vec;
   typedef double* Mat;
@@ -255,10 +273,12 @@ struct BdfStoreLocal
   PRX_MEM Mat A() { return A_; }
   PRX_MEM double* savedJ() { return savedJ_; }
   PRX_MEM int* piv() { return piv_; }
+  template <class MA, class VB>
+  PRX_MEM void getrs(MA a, const int* p, VB b);
 };
 
 template <int STRIDE, bool A_SMEM>
-struct BdfStoreSmem
+struct BdfStoreSmem : public SerialOwner
 {
   typedef SVecT<STRIDE> Vec;
   typedef typename std::conditional<A_SMEM, SVecT<STRIDE>, double*>::type Mat;
@@ -282,6 +302,42 @@ struct BdfStoreSmem
   PRX_MEM Mat A() { return A(std::integral_constant<bool, A_SMEM>()); }
   PRX_MEM double* savedJ() { return savedJ_; }
   PRX_MEM int* piv() { return piv_; }
+  template <class MA, class VB>
+  PRX_MEM void getrs(MA a, const int* p, VB b);
+};
+
+// Hot/cold split, one cell per thread: the vectors every Newton iteration touches (zn0, zn1, ewt, acor, ftemp,
+// y, delta [+ N species scratch]) are shared-memory columns, everything touched once per step or per linear
+// setup (zn[2..], tempv, the Newton matrix A) is a column of a GLOBAL scratch buffer (coalesced: element i of a
+// vector at cold[i*STRIDE], L2 resident), savedJ / pivots stay thread-local.  560 B of shared memory per LiDryer
+// cell instead of 952 / 1752 -> 12 resident warps per SM instead of 7 / 4.
+template <int STRIDE, bool SCRATCH>
+struct BdfStoreHot : public SerialOwner
+{
+  typedef SVecT<STRIDE> Vec;
+  typedef SVecT<STRIDE> Mat;
+  double* hot;
+  double* cold;
+  int nz;
+  double savedJ_[NEQ * NEQ];
+  int piv_[NEQ];
+  static PRX_HD int hot_doubles() { return 7 * NEQ + (SCRATCH ? N : 0); }
+  static PRX_HD int cold_doubles(const int qmax) { return (qmax > 1 ? qmax - 1 : 0) * NEQ + NEQ + NEQ * NEQ; }
+  PRX_MEM Vec hslot(const int s) const { return Vec{hot + s * NEQ * STRIDE}; }
+  PRX_MEM Vec cslot(const int s) const { return Vec{cold + s * NEQ * STRIDE}; }
+  PRX_MEM Vec zn(const int j) const { return (j < 2) ? hslot(j) : cslot(j - 2); }
+  PRX_MEM Vec ewt() const { return hslot(2); }
+  PRX_MEM Vec acor() const { return hslot(3); }
+  PRX_MEM Vec ftemp() const { return hslot(4); }
+  PRX_MEM Vec y() const { return hslot(5); }
+  PRX_MEM Vec delta() const { return hslot(6); }
+  PRX_MEM Vec scratch() const { return hslot(7); }
+  PRX_MEM Vec tempv() const { return cslot(nz - 2); }
+  PRX_MEM Mat A() const { return cslot(nz - 1); }
+  PRX_MEM double* savedJ() { return savedJ_; }
+  PRX_MEM int* piv() { return piv_; }
+  template <class MA, class VB>
+  PRX_MEM void getrs(MA a, const int* p, VB b);
 };
 
 template <class Store, class Src = CellSrc>
@@ -324,15 +380,15 @@ constexpr double UROUND = 2.220446049250313e-16;
 constexpr int FIRST_CALL = 6, PREV_CONV_FAIL = 7, PREV_ERR_FAIL = 8;
 constexpr int NLS_CONTINUE = 901, NLS_CONV_RECVR = 902;
 
-template <class VX, class VW>
-PRX_DEV double wrms(VX x, VW w)
+template <class Cell, class VX, class VW>
+PRX_DEV double wrms(Cell& s, VX x, VW w)
 {
   double sum = 0.0;
-  PRX_VLOOP
-  for (int i = 0; i < NEQ; i++) {
+  PRX_VEC_FOR(i) {
     const double pr = x[i] * w[i];
     sum += pr * pr;
   }
+  sum = s.gsum(sum);
   return sqrt(sum / NEQ);
 }
 
@@ -340,17 +396,16 @@ template <class Cell, class VY>
 PRX_DEV int ewt_set(Cell& s, const BdfParams& p, VY ycur)
 {
   int bad = 0;
-  PRX_VLOOP
-  for (int i = 0; i < NEQ; i++) {
+  PRX_VEC_FOR(i) {
     const double v = p.rtol * fabs(ycur[i]) + p.atolv[i];
     bad |= !(v > 0.0);
     s.tempv()[i] = v;
   }
+  bad = s.gor(bad);
   if (bad) {
     return -1;
   }
-  PRX_VLOOP
-  for (int i = 0; i < NEQ; i++) {
+  PRX_VEC_FOR(i) {
     s.ewt()[i] = 1.0 / s.tempv()[i];
   }
   return 0;
@@ -372,8 +427,7 @@ PRX_DEV void bdf_rescale(Cell& s)
 {
   double factor = s.eta;
   for (int j = 1; j <= s.q; j++) {
-    PRX_VLOOP
-    for (int i = 0; i < NEQ; i++) {
+    PRX_VEC_FOR(i) {
       s.zn(j)[i] *= factor;
     }
     factor *= s.eta;
@@ -406,14 +460,12 @@ PRX_DEV void bdf_increase_order(Cell& s, const int qmax)
     }
   }
   const double A1 = (-alpha0 - alpha1) / prod;
-  PRX_VLOOP
-  for (int i = 0; i < NEQ; i++) {
+  PRX_VEC_FOR(i) {
     s.zn(s.L)[i] = A1 * s.zn(s.indx_acor)[i];
   }
   if (s.q > 1) {
     for (int j = 2; j <= s.q; j++) {
-      PRX_VLOOP
-      for (int i = 0; i < NEQ; i++) {
+      PRX_VEC_FOR(i) {
         s.zn(j)[i] += s.l[j] * s.zn(s.L)[i];
       }
     }
@@ -437,8 +489,7 @@ PRX_DEV void bdf_decrease_order(Cell& s, const int qmax)
   }
   if (s.q > 2) {
     for (int j = 2; j < s.q; j++) {
-      PRX_VLOOP
-      for (int i = 0; i < NEQ; i++) {
+      PRX_VEC_FOR(i) {
         s.zn(j)[i] += -s.l[j] * s.zn(s.q)[i];
       }
     }
@@ -464,8 +515,7 @@ PRX_DEV void bdf_predict(Cell& s)
   s.tn += s.h;
   for (int k = 1; k <= s.q; k++) {
     for (int j = s.q; j >= k; j--) {
-      PRX_VLOOP
-      for (int i = 0; i < NEQ; i++) {
+      PRX_VEC_FOR(i) {
         s.zn(j - 1)[i] = s.zn(j - 1)[i] + s.zn(j)[i];
       }
     }
@@ -478,8 +528,7 @@ PRX_DEV void bdf_restore(Cell& s)
   s.tn = s.saved_t;
   for (int k = 1; k <= s.q; k++) {
     for (int j = s.q; j >= k; j--) {
-      PRX_VLOOP
-      for (int i = 0; i < NEQ; i++) {
+      PRX_VEC_FOR(i) {
         s.zn(j - 1)[i] = s.zn(j - 1)[i] - s.zn(j)[i];
       }
     }
@@ -629,6 +678,25 @@ PRX_DEV void dense_getrs(MA a, const int* p, VB b)
   b[0] /= a[0];
 }
 
+template <class MA, class VB>
+PRX_MEM void BdfStoreLocal::getrs(MA a, const int* p, VB b)
+{
+  dense_getrs(a, p, b);
+}
+template <int STRIDE, bool A_SMEM>
+template <class MA, class VB>
+PRX_MEM void BdfStoreSmem<STRIDE, A_SMEM>::getrs(MA a, const int* p, VB b)
+{
+  dense_getrs(a, p, b);
+}
+
+template <int STRIDE, bool SCRATCH>
+template <class MA, class VB>
+PRX_MEM void BdfStoreHot<STRIDE, SCRATCH>::getrs(MA a, const int* p, VB b)
+{
+  dense_getrs(a, p, b);
+}
+
 template <class Cell>
 PRX_DEV void bdf_set_eta(Cell& s)
 {
@@ -668,18 +736,17 @@ PRX_DEV void bdf_prepare_next_step(Cell& s, const int qmax)
   s.qwait = 2;
   double etaqm1 = 0.0;
   if (s.q > 1) {
-    const double ddn = wrms(s.zn(s.q), s.ewt()) * s.tq[1];
+    const double ddn = wrms(s, s.zn(s.q), s.ewt()) * s.tq[1];
     etaqm1 = 1.0 / (rpowerR(6.0 * ddn, 1.0 / s.q) + 0.000001);
   }
   double etaqp1 = 0.0;
   if (s.q != qmax) {
     if (s.saved_tq5 != 0.0) {
       const double cquot = (s.tq[5] / s.saved_tq5) * rpowerI(s.h / s.tau[2], s.L);
-      PRX_VLOOP
-      for (int i = 0; i < NEQ; i++) {
+      PRX_VEC_FOR(i) {
         s.tempv()[i] = -cquot * s.zn(qmax)[i] + s.acor()[i];
       }
-      const double dup = wrms(s.tempv(), s.ewt()) * s.tq[3];
+      const double dup = wrms(s, s.tempv(), s.ewt()) * s.tq[3];
       etaqp1 = 1.0 / (rpowerR(10.0 * dup, 1.0 / (s.L + 1)) + 0.000001);
     }
   }
@@ -696,8 +763,7 @@ PRX_DEV void bdf_prepare_next_step(Cell& s, const int qmax)
   } else {
     s.eta = etaqp1;
     s.qprime = s.q + 1;
-    PRX_VLOOP
-    for (int i = 0; i < NEQ; i++) {
+    PRX_VEC_FOR(i) {
       s.zn(qmax)[i] = s.acor()[i];
     }
   }
@@ -755,8 +821,7 @@ PRX_DEV int bdf_resume(Cell& s, const BdfParams& p)
     // ---- first call block of CVode ----
     if (ewt_set(s, p, s.zn(0)) != 0) {
       s.flag = CV_ILL_INPUT;
-      PRX_VLOOP
-      for (int i = 0; i < NEQ; i++) {
+      PRX_VEC_FOR(i) {
         s.y()[i] = s.zn(0)[i];
       }
       break;
@@ -769,21 +834,20 @@ PRX_DEV int bdf_resume(Cell& s, const BdfParams& p)
       const double tround = UROUND * fmax(fabs(s.tn), fabs(s.tout));
       if (s.tout == s.tn || tdist < 2.0 * tround) {
         s.flag = CV_TOO_CLOSE;
-        PRX_VLOOP
-        for (int i = 0; i < NEQ; i++) {
+        PRX_VEC_FOR(i) {
           s.y()[i] = s.zn(0)[i];
         }
         break;
       }
       s.hlb = 100.0 * tround;
       double hub_inv = 0.0;
-      PRX_VLOOP
-      for (int i = 0; i < NEQ; i++) {
+      PRX_VEC_FOR(i) {
         const double t2 = fabs(s.zn(0)[i]);
         const double t1 = 0.1 * t2 + 1.0 / s.ewt()[i];
         const double r = fabs(s.zn(1)[i]) / t1;
         hub_inv = (r > hub_inv) ? r : hub_inv;
       }
+      hub_inv = s.gmax(hub_inv);
       s.hub = 0.1 * tdist;
       if (s.hub * hub_inv > 1.0) {
         s.hub = 1.0 / hub_inv;
@@ -795,19 +859,17 @@ PRX_DEV int bdf_resume(Cell& s, const BdfParams& p)
     } else {
       s.hnew = s.hg;
       for (s.count1 = 1; s.count1 <= 4; s.count1++) {
-        PRX_VLOOP
-        for (int i = 0; i < NEQ; i++) {
+        PRX_VEC_FOR(i) {
           s.y()[i] = s.hg * s.zn(1)[i] + s.zn(0)[i];
         }
         PRX_YIELD_RHS(2, s.tn + s.hg, V_Y, V_TEMPV);
         s.nfe++;
         {
           const double ihg = 1.0 / s.hg;
-          PRX_VLOOP
-          for (int i = 0; i < NEQ; i++) {
+          PRX_VEC_FOR(i) {
             s.tempv()[i] = ihg * (s.tempv()[i] - s.zn(1)[i]); // N_VLinearSum a == -b: a*(x-y)
           }
-          const double yddnrm = wrms(s.tempv(), s.ewt());
+          const double yddnrm = wrms(s, s.tempv(), s.ewt());
           s.hnew = (yddnrm * s.hub * s.hub > 2.0) ? sqrt(2.0 / yddnrm) : sqrt(s.hg * s.hub);
           if (s.count1 == 4) {
             break;
@@ -834,8 +896,7 @@ PRX_DEV int bdf_resume(Cell& s, const BdfParams& p)
     }
     s.hscale = s.h;
     s.hprime = s.h;
-    PRX_VLOOP
-    for (int i = 0; i < NEQ; i++) {
+    PRX_VEC_FOR(i) {
       s.zn(1)[i] *= s.h;
     }
     s.nstloc = 0;
@@ -851,7 +912,7 @@ PRX_DEV int bdf_resume(Cell& s, const BdfParams& p)
         s.flag = CV_TOO_MUCH_WORK;
         break;
       }
-      if (UROUND * wrms(s.zn(0), s.ewt()) > 1.0) {
+      if (UROUND * wrms(s, s.zn(0), s.ewt()) > 1.0) {
         s.flag = CV_TOO_MUCH_ACC;
         break;
       }
@@ -878,20 +939,17 @@ PRX_DEV int bdf_resume(Cell& s, const BdfParams& p)
         s.jbad_nls = 0;
         s.nls_jcur = 0;
         s.nls_ok = 0;
-        PRX_VLOOP
-        for (int i = 0; i < NEQ; i++) {
+        PRX_VEC_FOR(i) {
           s.acor()[i] = 0.0;
         }
         for (;;) { // Newton attempts (second pass: with a fresh Jacobian)
           s.curiter = 0;
-          PRX_VLOOP
-          for (int i = 0; i < NEQ; i++) {
+          PRX_VEC_FOR(i) {
             s.y()[i] = s.zn(0)[i] + s.acor()[i];
           }
           PRX_YIELD_RHS(3, s.tn, V_Y, V_FTEMP);
           s.nfe++;
-          PRX_VLOOP
-          for (int i = 0; i < NEQ; i++) {
+          PRX_VEC_FOR(i) {
             double d = s.rl1 * s.zn(1)[i] + s.acor()[i];
             d = -s.gamma * s.ftemp()[i] + d;
             s.delta()[i] = d;
@@ -914,28 +972,32 @@ PRX_DEV int bdf_resume(Cell& s, const BdfParams& p)
               } else {
                 // cvLsDenseDQJac
                 {
-                  const double fnorm = wrms(s.ftemp(), s.ewt());
+                  const double fnorm = wrms(s, s.ftemp(), s.ewt());
                   s.minInc = (fnorm != 0.0) ? (1000.0 * fabs(s.h) * UROUND * NEQ * fnorm) : 1.0;
                 }
                 for (s.jcol = 0; s.jcol < NEQ; s.jcol++) {
+                  s.sync();
                   s.yjsaved = s.y()[s.jcol];
                   s.inc = fmax(sqrt(UROUND) * fabs(s.yjsaved), s.minInc / s.ewt()[s.jcol]);
-                  s.y()[s.jcol] += s.inc;
+                  s.sync();
+                  if (s.owns(s.jcol)) {
+                    s.y()[s.jcol] += s.inc;
+                  }
                   PRX_YIELD_RHS(5, s.tn, V_Y, V_TEMPV);
                   s.nfeDQ++;
-                  s.y()[s.jcol] = s.yjsaved;
+                  if (s.owns(s.jcol)) {
+                    s.y()[s.jcol] = s.yjsaved;
+                  }
                   {
                     const double inc_inv = 1.0 / s.inc;
-                    PRX_VLOOP
-                    for (int i = 0; i < NEQ; i++) {
+                    PRX_VEC_FOR(i) {
                       s.savedJ()[s.jcol * NEQ + i] = inc_inv * (s.tempv()[i] - s.ftemp()[i]);
                     }
                   }
                 }
                 // the RHS may use delta as scratch (shared-memory kernels): rebuild the Newton residual,
                 // same operands and operations as above, hence the same bits
-                PRX_VLOOP
-                for (int i = 0; i < NEQ; i++) {
+                PRX_VEC_FOR(i) {
                   double d = s.rl1 * s.zn(1)[i] + s.acor()[i];
                   d = -s.gamma * s.ftemp()[i] + d;
                   s.delta()[i] = d;
@@ -948,17 +1010,15 @@ PRX_DEV int bdf_resume(Cell& s, const BdfParams& p)
             // scales by -gamma and adds the identity: the same two roundings per entry)
             {
               const double mg = -s.gamma;
+              s.sync();
               PRX_MLOOP
-              for (int j = 0; j < NEQ; j++) {
-                PRX_VLOOP
-                for (int i = 0; i < NEQ; i++) {
-                  double v = s.savedJ()[j * NEQ + i];
-                  v *= mg;
-                  if (i == j) {
-                    v += 1.0;
-                  }
-                  s.A()[j * NEQ + i] = v;
+              for (int e = s.vbegin(); e < NEQ * NEQ; e += s.vstep()) {
+                double v = s.savedJ()[e];
+                v *= mg;
+                if (e % (NEQ + 1) == 0) { // diagonal of the column-major matrix
+                  v += 1.0;
                 }
+                s.A()[e] = v;
               }
             }
             PRX_YIELD(6, REQ_LU); // kernel factors A in place, sets piv and lu_info
@@ -975,31 +1035,28 @@ PRX_DEV int bdf_resume(Cell& s, const BdfParams& p)
           if (s.retval == 0) {
             for (;;) { // Newton iterations
               s.nni++;
-              PRX_VLOOP
-              for (int i = 0; i < NEQ; i++) {
+              PRX_VEC_FOR(i) {
                 s.delta()[i] = -s.delta()[i];
               }
-              dense_getrs(s.A(), s.piv(), s.delta());
+              s.getrs(s.A(), s.piv(), s.delta());
               if (s.gamrat != 1.0) {
                 const double sc = 2.0 / (1.0 + s.gamrat);
-                PRX_VLOOP
-                for (int i = 0; i < NEQ; i++) {
+                PRX_VEC_FOR(i) {
                   s.delta()[i] *= sc;
                 }
               }
-              PRX_VLOOP
-              for (int i = 0; i < NEQ; i++) {
+              PRX_VEC_FOR(i) {
                 s.acor()[i] = s.acor()[i] + s.delta()[i];
               }
               {
-                const double del = wrms(s.delta(), s.ewt());
+                const double del = wrms(s, s.delta(), s.ewt());
                 const int m = s.curiter;
                 if (m > 0) {
                   s.crate = fmax(0.3 * s.crate, del / s.delp);
                 }
                 const double dcon = del * fmin(1.0, s.crate) / s.tq[4];
                 if (dcon <= 1.0) {
-                  s.acnrm = (m == 0) ? del : wrms(s.acor(), s.ewt());
+                  s.acnrm = (m == 0) ? del : wrms(s, s.acor(), s.ewt());
                   s.nls_ok = 1;
                   s.retval = 0;
                 } else if ((m >= 1) && (del > 2.0 * s.delp)) {
@@ -1017,14 +1074,12 @@ PRX_DEV int bdf_resume(Cell& s, const BdfParams& p)
                 s.retval = NLS_CONV_RECVR;
                 break;
               }
-              PRX_VLOOP
-              for (int i = 0; i < NEQ; i++) {
+              PRX_VEC_FOR(i) {
                 s.y()[i] = s.zn(0)[i] + s.acor()[i];
               }
               PRX_YIELD_RHS(7, s.tn, V_Y, V_FTEMP);
               s.nfe++;
-              PRX_VLOOP
-              for (int i = 0; i < NEQ; i++) {
+              PRX_VEC_FOR(i) {
                 double d = s.rl1 * s.zn(1)[i] + s.acor()[i];
                 d = -s.gamma * s.ftemp()[i] + d;
                 s.delta()[i] = d;
@@ -1037,8 +1092,7 @@ PRX_DEV int bdf_resume(Cell& s, const BdfParams& p)
           if ((s.retval > 0) && !s.nls_jcur) {
             s.callSetup = 1;
             s.jbad_nls = 1;
-            PRX_VLOOP
-            for (int i = 0; i < NEQ; i++) {
+            PRX_VEC_FOR(i) {
               s.acor()[i] = 0.0;
             }
             continue;
@@ -1047,8 +1101,7 @@ PRX_DEV int bdf_resume(Cell& s, const BdfParams& p)
         }
         if (s.nls_ok) {
           s.jcur = 0;
-          PRX_VLOOP
-          for (int i = 0; i < NEQ; i++) {
+          PRX_VEC_FOR(i) {
             s.y()[i] = s.zn(0)[i] + s.acor()[i];
           }
         } else {
@@ -1104,8 +1157,7 @@ PRX_DEV int bdf_resume(Cell& s, const BdfParams& p)
         s.qwait = 10;
         PRX_YIELD_RHS(8, s.tn, V_ZN0, V_TEMPV);
         s.nfe++;
-        PRX_VLOOP
-        for (int i = 0; i < NEQ; i++) {
+        PRX_VEC_FOR(i) {
           s.zn(1)[i] = s.h * s.tempv()[i];
         }
       }
@@ -1125,15 +1177,13 @@ PRX_DEV int bdf_resume(Cell& s, const BdfParams& p)
       s.tau[1] = s.h;
       for (int j = 0; j <= s.q; j++) {
         const double lj = s.l[j];
-        PRX_VLOOP
-        for (int i = 0; i < NEQ; i++) {
+        PRX_VEC_FOR(i) {
           s.zn(j)[i] += lj * s.acor()[i];
         }
       }
       s.qwait--;
       if ((s.qwait == 1) && (s.q != p.qmax)) {
-        PRX_VLOOP
-        for (int i = 0; i < NEQ; i++) {
+        PRX_VEC_FOR(i) {
           s.zn(p.qmax)[i] = s.acor()[i];
         }
         s.saved_tq5 = s.tq[5];
@@ -1143,8 +1193,7 @@ PRX_DEV int bdf_resume(Cell& s, const BdfParams& p)
       s.etamax = 10.0;
       {
         const double t2 = s.tq[2];
-        PRX_VLOOP
-        for (int i = 0; i < NEQ; i++) {
+        PRX_VEC_FOR(i) {
           s.acor()[i] *= t2;
         }
       }
@@ -1161,8 +1210,7 @@ PRX_DEV int bdf_resume(Cell& s, const BdfParams& p)
           }
           cvals[nvec++] = c;
         }
-        PRX_VLOOP
-        for (int i = 0; i < NEQ; i++) {
+        PRX_VEC_FOR(i) {
           double z = cvals[0] * s.zn(s.q)[i];
           for (int j = 1; j < nvec; j++) {
             z += cvals[j] * s.zn(s.q - j)[i];
@@ -1174,8 +1222,7 @@ PRX_DEV int bdf_resume(Cell& s, const BdfParams& p)
       }
     }
     // failure exits: the reference ignores CVode's flag on the CPU path and keeps yout = zn[0]
-    PRX_VLOOP
-    for (int i = 0; i < NEQ; i++) {
+    PRX_VEC_FOR(i) {
       s.y()[i] = s.zn(0)[i];
     }
     break;

@@ -20,6 +20,7 @@
 
 #include "prx_integrators.cuh"
 #include "prx_tchem.cuh"
+#include "prx_coop.cuh"
 #include "prx_kernels.cuh"
 
 #ifndef PRX_BLOCK
@@ -391,8 +392,6 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
 //    warps (as many as the shared memory holds: launch_bdf computes it with the occupancy API);
 //  * the external species source is not copied per cell, it is re-read (coalesced, L2-resident)
 //    through SrcRef at every RHS.
-#define PRX_HAVE_BDF2 (PRX_NUM_SPECIES <= 32) // one cell per thread stops making sense beyond that
-#if PRX_HAVE_BDF2
 struct SrcRef
 {
   double rhoe_init, rhoesrc;
@@ -401,6 +400,9 @@ struct SrcRef
 };
 
 extern __shared__ double prx_dyn_smem[];
+
+#define PRX_HAVE_BDF2 (PRX_NUM_SPECIES <= 32) // one cell per thread stops making sense beyond that
+#if PRX_HAVE_BDF2
 
 template <bool A_SMEM>
 __global__ void __launch_bounds__(32) PRX_CAT(bdf2_kernel_, PRX_MECH_SUFFIX)(
@@ -598,7 +600,541 @@ cudaError_t launch_bdf2(const BoxArgs& a, const BdfParams& p, const SchedParams&
   kern<<<(int)grid, 32, smem, stream>>>(a, p, sp, queue, stats);
   return cudaGetLastError();
 }
+#ifndef PRX_BDF3_MINBLOCKS
+#define PRX_BDF3_MINBLOCKS 12
+#endif
+// hot/cold split (BdfStoreHot); TABRHS: table-driven RHS (rolled) instead of the generated straight-line one
+template <bool TABRHS>
+__global__ void __launch_bounds__(32, PRX_BDF3_MINBLOCKS) PRX_CAT(bdf3_kernel_, PRX_MECH_SUFFIX)(
+  const BoxArgs a, const BdfParams p, const SchedParams sp, int* __restrict__ queue, DevStats* __restrict__ stats,
+  double* __restrict__ cold, const int cold_doubles)
+{
+  typedef BdfCellT<BdfStoreHot<32, TABRHS>, SrcRef> Cell;
+  Cell s;
+  s.hot = prx_dyn_smem + threadIdx.x;
+  s.cold = cold + (size_t)blockIdx.x * 32 * cold_doubles + threadIdx.x;
+  s.nz = p.qmax + 1;
+  int cell = -1;
+  bool exhausted = false;
+  int req = REQ_NONE;
+  LaneStats ls = {};
+  BdfParams pc = p;
+  pc.array4_semantics = 0; // the initial T solve is done here with the table-driven Newton loop
+  for (;;) {
+    // ---- (1) refill ----
+    const int got = fetch_cell((cell < 0) && !exhausted, queue, a.ncells);
+    if (got == -2) {
+      exhausted = true;
+    } else if (got >= 0) {
+      double y0[NEQ];
+      CellSrc cs;
+      if (load_cell(a, got, y0, cs, p.clean_init_massfrac)) {
+        cell = got;
+        s.src.rhoe_init = cs.rhoe_init;
+        s.src.rhoesrc = cs.rhoesrc;
+        if (a.layout == LAYOUT_ARRAY4) {
+          s.src.p = a.rYsrc.p + cell_offset(got, a.len, a.rYsrc.js, a.rYsrc.ks);
+          s.src.stride = a.rYsrc.ns;
+        } else {
+          s.src.p = a.ysrc + (long long)got * N;
+          s.src.stride = 1;
+        }
+        double rho = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+          s.zn(0)[k] = y0[k];
+          rho += y0[k];
+        }
+        double temp = y0[N];
+        if (p.array4_semantics) { // box_flatten re-solves T from (e, Y) (ReactorUtils.H:206-219)
+          const double rho_inv = 1.0 / rho;
+          if (TABRHS) {
+#pragma unroll
+            for (int k = 0; k < N; k++) {
+              s.scratch()[k] = y0[k] * rho_inv;
+            }
+            t_from_energy_tab<TabC>(p.reactor_type, cs.rhoe_init * rho_inv, s.scratch(), temp);
+          } else {
+            double Y[N];
+#pragma unroll
+            for (int k = 0; k < N; k++) {
+              Y[k] = y0[k] * rho_inv;
+            }
+            t_from_energy(p.reactor_type, cs.rhoe_init * rho_inv, Y, temp);
+          }
+        }
+        s.zn(0)[N] = temp;
+        bdf_begin(s, pc, a.dt, a.time);
+        req = REQ_NONE;
+      } else {
+        store_masked(a, got);
+        ls.masked++;
+      }
+    }
+    if (!__any_sync(FULL, !(exhausted && (cell < 0)))) {
+      break;
+    }
+    // ---- (2) control ----
+    if (cell >= 0 && req == REQ_NONE) {
+      req = bdf_resume(s, pc);
+    }
+    __syncwarp();
+    // ---- (3) serve ----
+    const unsigned m_rhs = __ballot_sync(FULL, req == REQ_RHS);
+    const unsigned m_jac = __ballot_sync(FULL, req == REQ_JAC);
+    const unsigned m_lu = __ballot_sync(FULL, req == REQ_LU);
+    if (req == REQ_RHS) {
+      const SrcScalars sc{s.src.rhoe_init, s.src.rhoesrc};
+      const double* sp_p = s.src.p;
+      const long long sp_s = s.src.stride;
+      if (TABRHS) {
+        rhs_tab<TabC>(
+          s.t_eval, p.reactor_type, s.vec(s.in_sel), s.vec(s.out_sel), s.scratch(), s.delta(), sc,
+          [sp_p, sp_s](const int n) { return __ldg(sp_p + n * sp_s); });
+      } else {
+        double yy[NEQ], yd[NEQ];
+        CellSrc cs;
+        cs.rhoe_init = sc.rhoe_init;
+        cs.rhoesrc = sc.rhoesrc;
+        typename Cell::Vec vin = s.vec(s.in_sel);
+#pragma unroll
+        for (int k = 0; k < NEQ; k++) {
+          yy[k] = vin[k];
+        }
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+          cs.rYsrc[k] = __ldg(sp_p + k * sp_s);
+        }
+        rhs(s.t_eval, p.reactor_type, yy, yd, cs);
+        typename Cell::Vec vout = s.vec(s.out_sel);
+#pragma unroll
+        for (int k = 0; k < NEQ; k++) {
+          vout[k] = yd[k];
+        }
+      }
+      req = REQ_NONE;
+    }
+    __syncwarp();
+    if (m_jac && ((__popc(m_jac) >= sp.jac_defer_min_lanes) || (m_rhs == 0))) {
+      if (req == REQ_JAC) {
+        double yy[NEQ];
+#pragma unroll
+        for (int k = 0; k < NEQ; k++) {
+          yy[k] = s.y()[k];
+        }
+        double* J = s.savedJ();
+        jac_analytic(p.reactor_type, yy, J, [J](const int row, const int col, const double v) { J[col * NEQ + row] = v; });
+        req = REQ_NONE;
+      }
+      __syncwarp();
+    }
+    if (m_lu && ((__popc(m_lu) >= sp.lu_defer_min_lanes) || (m_rhs == 0))) {
+      if (req == REQ_LU) {
+        s.lu_info = dense_getrf(s.A(), s.piv());
+        req = REQ_NONE;
+      }
+      __syncwarp();
+    }
+    if (req == REQ_DONE) {
+      // box_unflatten (ReactorUtils.H:222-291)
+      const double rhoe_out = s.src.rhoe_init + a.dt * s.src.rhoesrc;
+      const double fc = double(s.nfe + s.nfeDQ);
+      if (a.layout == LAYOUT_ARRAY4) {
+        const long long o = cell_offset(cell, a.len, a.rY.js, a.rY.ks);
+        double rho = 0.0;
+        if (p.clean_init_massfrac) {
+          double rho_old = 0.0, rho_oldclipped = 0.0;
+          for (int k = 0; k < N; k++) {
+            rho_old += a.rY.p[o + k * a.rY.ns];
+          }
+          for (int k = 0; k < N; k++) {
+            rho_oldclipped += fmin(fmax(0.0, a.rY.p[o + k * a.rY.ns]), rho_old);
+          }
+          for (int k = 0; k < N; k++) {
+            const double yold = a.rY.p[o + k * a.rY.ns];
+            const double clipped = fmin(fmax(0.0, yold), rho_old);
+            s.y()[k] = yold + (s.y()[k] - clipped) * rho_old / rho_oldclipped;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+          const double v = s.y()[k];
+          a.rY.p[o + k * a.rY.ns] = v;
+          rho += v;
+        }
+        const double rho_inv = 1.0 / rho;
+        double temp = s.y()[N];
+        if (TABRHS) {
+#pragma unroll
+          for (int k = 0; k < N; k++) {
+            s.scratch()[k] = s.y()[k] * rho_inv;
+          }
+          t_from_energy_tab<TabC>(p.reactor_type, rhoe_out * rho_inv, s.scratch(), temp);
+        } else {
+          double Y[N];
+#pragma unroll
+          for (int k = 0; k < N; k++) {
+            Y[k] = s.y()[k] * rho_inv;
+          }
+          t_from_energy(p.reactor_type, rhoe_out * rho_inv, Y, temp);
+        }
+        a.rE.p[cell_offset(cell, a.len, a.rE.js, a.rE.ks)] = rhoe_out;
+        a.T.p[cell_offset(cell, a.len, a.T.js, a.T.ks)] = temp;
+        a.FC.p[cell_offset(cell, a.len, a.FC.js, a.FC.ks)] = fc;
+      } else {
+#pragma unroll
+        for (int k = 0; k < NEQ; k++) {
+          a.y[(long long)cell * NEQ + k] = s.y()[k];
+        }
+        a.e[cell] = rhoe_out;
+        if (a.fc != nullptr) {
+          a.fc[cell] = fc;
+        }
+      }
+      ls.cells++;
+      ls.steps += s.nst;
+      ls.rhs += s.nfe + s.nfeDQ;
+      ls.jac += s.nje;
+      ls.setups += s.nsetups;
+      ls.newton += s.nni;
+      ls.errfail += s.netf;
+      ls.convfail += s.ncfn;
+      ls.failed += (s.flag != CV_SUCCESS);
+      ls.maxsteps = (unsigned long long)s.nst > ls.maxsteps ? s.nst : ls.maxsteps;
+      cell = -1;
+      req = REQ_NONE;
+    }
+  }
+  flush_stats(ls, stats);
+}
+
+template <bool TABRHS>
+cudaError_t launch_bdf3(const BoxArgs& a, const BdfParams& p, const SchedParams& sp, int* queue, DevStats* stats, cudaStream_t stream)
+{
+  typedef BdfStoreHot<32, TABRHS> Store;
+  auto kern = PRX_CAT(bdf3_kernel_, PRX_MECH_SUFFIX)<TABRHS>;
+  const size_t smem = sizeof(double) * 32 * (size_t)Store::hot_doubles();
+  const int cold_doubles = Store::cold_doubles(p.qmax);
+  int dev = 0, sms = 148, per_sm = 0, max_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (smem > (size_t)max_optin) {
+    return cudaErrorInvalidConfiguration;
+  }
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    return e;
+  }
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem) != cudaSuccess || per_sm < 1) {
+    return cudaErrorInvalidConfiguration;
+  }
+  if (sp.max_warps_per_sm > 0 && per_sm > sp.max_warps_per_sm) {
+    per_sm = sp.max_warps_per_sm;
+  }
+  long long grid = (long long)sms * per_sm; // persistent: one full wave, a multiple of the SM count
+  const long long needed = ((long long)a.ncells + 31) / 32;
+  grid = needed < grid ? needed : grid;
+  double* cold = nullptr; // cold columns of the resident cells (stream-ordered, pool-backed after the first call)
+  e = cudaMallocAsync(&cold, sizeof(double) * (size_t)grid * 32 * cold_doubles, stream);
+  if (e != cudaSuccess) {
+    return e;
+  }
+  e = cudaMemsetAsync(queue, 0, sizeof(int), stream);
+  if (e == cudaSuccess) {
+    kern<<<(int)grid, 32, smem, stream>>>(a, p, sp, queue, stats, cold, cold_doubles);
+    e = cudaGetLastError();
+  }
+  const cudaError_t e2 = cudaFreeAsync(cold, stream);
+  return e != cudaSuccess ? e : e2;
+}
 #endif // PRX_HAVE_BDF2
+
+// =====================================================================================
+// BDF kernel, third generation: G lanes per cell (prx_coop.cuh)
+// =====================================================================================
+// Same warp loop as above (refill / control / serve) with the GROUP as the unit: the 32/G cells of a warp
+// run their integrator coroutines (control flow replicated in the G lanes of a group, uniform inside it) and
+// meet at one converged place per request kind.  Blocks are single warps; no block barrier.
+#define PRX_HAVE_COOP 1
+#if PRX_HAVE_COOP
+// -DPRX_COOP_SERIAL_JAC: debugging aid - the analytic Jacobian evaluated by ONE lane with the generated
+// straight-line code instead of jac_coop (small mechanisms only)
+
+#ifndef PRX_COOP_MINBLOCKS
+#define PRX_COOP_MINBLOCKS 16
+#endif
+
+#ifdef PRX_COOP_SERIAL_JAC
+__device__ __noinline__ void jac_serial(const int reactor_type, const double* __restrict__ y, double* __restrict__ J)
+{
+  double yy[NEQ];
+  double Jt[NEQ * NEQ];
+  for (int k = 0; k < NEQ; k++) {
+    yy[k] = y[k];
+  }
+  jac_analytic(reactor_type, yy, Jt, [J](const int row, const int col, const double v) { J[col * NEQ + row] = v; });
+}
+#endif
+
+template <int G>
+__global__ void __launch_bounds__(32, PRX_COOP_MINBLOCKS) PRX_CAT(bdfc_kernel_, PRX_MECH_SUFFIX)(
+  const BoxArgs a, const BdfParams p, const SchedParams sp, int* __restrict__ queue, DevStats* __restrict__ stats,
+  double* __restrict__ jscratch, const int cell_doubles)
+{
+  typedef BdfCellT<BdfStoreCoop<G>, SrcRef> Cell;
+  constexpr int CPW = 32 / G; // cells per warp
+  Cell s;
+  const unsigned lane = threadIdx.x & 31u;
+  const int grp = (int)lane / G;
+  const Grp<G>& g = s.g;
+  s.base = prx_dyn_smem + (size_t)grp * cell_doubles;
+  s.gJ = jscratch + ((size_t)blockIdx.x * CPW + grp) * (NEQ * NEQ);
+  s.nz = p.qmax + 1;
+  int cell = -1;
+  bool exhausted = false;
+  int req = REQ_NONE;
+  LaneStats ls = {};
+  BdfParams pc = p;
+  pc.array4_semantics = 0; // the initial T solve is done here, cooperatively
+  for (;;) {
+    // ---- (1) refill: the group leaders draw cell indices (one atomic per warp), then broadcast ----
+    int got = fetch_cell((cell < 0) && !exhausted && (g.gl == 0), queue, a.ncells);
+    got = __shfl_sync(FULL, got, (int)(lane & ~(unsigned)(G - 1)));
+    if (got == -2) {
+      exhausted = true;
+    } else if (got >= 0) {
+      bool live = true;
+      if (a.layout == LAYOUT_ARRAY4 && a.mask.p != nullptr) {
+        live = a.mask.p[cell_offset(got, a.len, a.mask.js, a.mask.ks)] != -1;
+      }
+      if (live) {
+        cell = got;
+        double* z0 = s.zn(0);
+        double temp;
+        if (a.layout == LAYOUT_ARRAY4) {
+          const long long o = cell_offset(got, a.len, a.rY.js, a.rY.ks);
+          s.src.p = a.rYsrc.p + cell_offset(got, a.len, a.rYsrc.js, a.rYsrc.ks);
+          s.src.stride = a.rYsrc.ns;
+          for (int k = g.gl; k < N; k += G) {
+            z0[k] = __ldg(a.rY.p + o + k * a.rY.ns);
+          }
+          temp = a.T.p[cell_offset(got, a.len, a.T.js, a.T.ks)];
+          s.src.rhoe_init = a.rE.p[cell_offset(got, a.len, a.rE.js, a.rE.ks)];
+          s.src.rhoesrc = a.rEsrc.p[cell_offset(got, a.len, a.rEsrc.js, a.rEsrc.ks)];
+        } else {
+          s.src.p = a.ysrc + (long long)got * N;
+          s.src.stride = 1;
+          for (int k = g.gl; k < N; k += G) {
+            z0[k] = a.y[(long long)got * NEQ + k];
+          }
+          temp = a.y[(long long)got * NEQ + N];
+          s.src.rhoe_init = a.e[got];
+          s.src.rhoesrc = a.esrc[got];
+        }
+        if (a.layout == LAYOUT_ARRAY4) { // box_flatten: optional clipping, then T from (e, Y)
+          double part = 0.0;
+          for (int k = g.gl; k < N; k += G) {
+            part += z0[k];
+          }
+          double rho = g.sum(part);
+          if (p.clean_init_massfrac) { // ReactorUtils.H:183-199: clip to [0, rho_old], density of the clipped state
+            part = 0.0;
+            for (int k = g.gl; k < N; k += G) {
+              z0[k] = fmin(fmax(0.0, z0[k]), rho);
+              part += z0[k];
+            }
+            rho = g.sum(part);
+          }
+          const double rho_inv = 1.0 / rho;
+          for (int k = g.gl; k < N; k += G) {
+            s.sc()[k] = z0[k] * rho_inv;
+          }
+          double cv_unused;
+          if (p.reactor_type == 1) {
+            t_from_energy_coop<TabG, 1, G>(g, s.src.rhoe_init * rho_inv, s.sc(), temp, cv_unused);
+          } else {
+            t_from_energy_coop<TabG, 2, G>(g, s.src.rhoe_init * rho_inv, s.sc(), temp, cv_unused);
+          }
+        }
+        if (s.owns(N)) {
+          z0[N] = temp;
+        }
+        g.sync();
+        bdf_begin(s, pc, a.dt, a.time);
+        req = REQ_NONE;
+      } else {
+        if (g.gl == 0) {
+          store_masked(a, got);
+          ls.masked++;
+        }
+      }
+    }
+    if (!__any_sync(FULL, !(exhausted && (cell < 0)))) {
+      break;
+    }
+    // ---- (2) control ----
+    if (cell >= 0 && req == REQ_NONE) {
+      req = bdf_resume(s, pc);
+    }
+    __syncwarp();
+    // ---- (3) serve ----
+    const unsigned m_rhs = __ballot_sync(FULL, req == REQ_RHS);
+    const unsigned m_jac = __ballot_sync(FULL, req == REQ_JAC);
+    const unsigned m_lu = __ballot_sync(FULL, req == REQ_LU);
+    if (req == REQ_RHS) {
+      const SrcScalars sc{s.src.rhoe_init, s.src.rhoesrc};
+      const double* sp_p = s.src.p;
+      const long long sp_s = s.src.stride;
+      rhs_coop<TabG, G>(
+        g, s.t_eval, p.reactor_type, s.vec(s.in_sel), s.vec(s.out_sel), s.sc(), s.gs(), s.qv(), sc,
+        [sp_p, sp_s](const int n) { return __ldg(sp_p + n * sp_s); });
+      req = REQ_NONE;
+    }
+    __syncwarp();
+    if (m_jac && ((__popc(m_jac) >= sp.jac_defer_min_lanes * G) || (m_rhs == 0))) {
+      if (req == REQ_JAC) {
+        g.sync();
+#ifdef PRX_COOP_SERIAL_JAC
+        if (g.gl == 0) {
+          jac_serial(p.reactor_type, s.y(), s.savedJ());
+        }
+        g.sync();
+#else
+        jac_coop<TabG, G>(g, p.reactor_type, s.y(), s.A(), s.sc(), s.gs(), s.dq(), s.qv(), s.savedJ());
+#endif
+        req = REQ_NONE;
+      }
+      __syncwarp();
+    }
+    if (m_lu && ((__popc(m_lu) >= sp.lu_defer_min_lanes * G) || (m_rhs == 0))) {
+      if (req == REQ_LU) {
+        s.lu_info = getrf_coop<G>(g, s.A(), s.piv());
+        req = REQ_NONE;
+      }
+      __syncwarp();
+    }
+    if (req == REQ_DONE) {
+      // box_unflatten (ReactorUtils.H:222-291)
+      g.sync();
+      const double rhoe_out = s.src.rhoe_init + a.dt * s.src.rhoesrc;
+      const double fc = double(s.nfe + s.nfeDQ);
+      double* yv = s.y();
+      if (a.layout == LAYOUT_ARRAY4) {
+        const long long o = cell_offset(cell, a.len, a.rY.js, a.rY.ks);
+        if (p.clean_init_massfrac) { // increment measured against the clipped input (ReactorUtils.H:244-271)
+          double p0 = 0.0;
+          for (int k = g.gl; k < N; k += G) {
+            p0 += a.rY.p[o + k * a.rY.ns];
+          }
+          const double rho_old = g.sum(p0);
+          double p1 = 0.0;
+          for (int k = g.gl; k < N; k += G) {
+            p1 += fmin(fmax(0.0, a.rY.p[o + k * a.rY.ns]), rho_old);
+          }
+          const double rho_oldclipped = g.sum(p1);
+          for (int k = g.gl; k < N; k += G) {
+            const double yold = a.rY.p[o + k * a.rY.ns];
+            const double clipped = fmin(fmax(0.0, yold), rho_old);
+            yv[k] = yold + (yv[k] - clipped) * rho_old / rho_oldclipped;
+          }
+        }
+        double part = 0.0;
+        for (int k = g.gl; k < N; k += G) {
+          const double v = yv[k];
+          a.rY.p[o + k * a.rY.ns] = v;
+          part += v;
+        }
+        const double rho = g.sum(part);
+        const double rho_inv = 1.0 / rho;
+        for (int k = g.gl; k < N; k += G) {
+          s.sc()[k] = yv[k] * rho_inv;
+        }
+        double temp = yv[N];
+        double cv_unused;
+        if (p.reactor_type == 1) {
+          t_from_energy_coop<TabG, 1, G>(g, rhoe_out * rho_inv, s.sc(), temp, cv_unused);
+        } else {
+          t_from_energy_coop<TabG, 2, G>(g, rhoe_out * rho_inv, s.sc(), temp, cv_unused);
+        }
+        if (g.gl == 0) {
+          a.rE.p[cell_offset(cell, a.len, a.rE.js, a.rE.ks)] = rhoe_out;
+          a.T.p[cell_offset(cell, a.len, a.T.js, a.T.ks)] = temp;
+          a.FC.p[cell_offset(cell, a.len, a.FC.js, a.FC.ks)] = fc;
+        }
+      } else {
+        for (int k = g.gl; k < NEQ; k += G) {
+          a.y[(long long)cell * NEQ + k] = yv[k];
+        }
+        if (g.gl == 0) {
+          a.e[cell] = rhoe_out;
+          if (a.fc != nullptr) {
+            a.fc[cell] = fc;
+          }
+        }
+      }
+      if (g.gl == 0) {
+        ls.cells++;
+        ls.steps += s.nst;
+        ls.rhs += s.nfe + s.nfeDQ;
+        ls.jac += s.nje;
+        ls.setups += s.nsetups;
+        ls.newton += s.nni;
+        ls.errfail += s.netf;
+        ls.convfail += s.ncfn;
+        ls.failed += (s.flag != CV_SUCCESS);
+        ls.maxsteps = (unsigned long long)s.nst > ls.maxsteps ? s.nst : ls.maxsteps;
+      }
+      cell = -1;
+      req = REQ_NONE;
+    }
+  }
+  flush_stats(ls, stats);
+}
+
+template <int G>
+cudaError_t launch_bdfc(const BoxArgs& a, const BdfParams& p, const SchedParams& sp, int* queue, DevStats* stats, cudaStream_t stream)
+{
+  auto kern = PRX_CAT(bdfc_kernel_, PRX_MECH_SUFFIX)<G>;
+  constexpr int CPW = 32 / G;
+  const int cell_doubles = BdfStoreCoop<G>::doubles_per_cell(p.qmax);
+  const size_t smem = sizeof(double) * (size_t)CPW * cell_doubles;
+  int dev = 0, sms = 148, per_sm = 0, max_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (smem > (size_t)max_optin) {
+    return cudaErrorInvalidConfiguration;
+  }
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    return e;
+  }
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem) != cudaSuccess || per_sm < 1) {
+    return cudaErrorInvalidConfiguration;
+  }
+  if (sp.max_warps_per_sm > 0 && per_sm > sp.max_warps_per_sm) {
+    per_sm = sp.max_warps_per_sm;
+  }
+  long long grid = (long long)sms * per_sm; // persistent: one full wave, a multiple of the SM count
+  const long long needed = ((long long)a.ncells + CPW - 1) / CPW;
+  grid = needed < grid ? needed : grid;
+  double* jscratch = nullptr; // savedJ slots, one per resident cell (stream-ordered, pool-backed after the first call)
+  e = cudaMallocAsync(&jscratch, sizeof(double) * (size_t)grid * CPW * NEQ * NEQ, stream);
+  if (e != cudaSuccess) {
+    return e;
+  }
+  e = cudaMemsetAsync(queue, 0, sizeof(int), stream);
+  if (e == cudaSuccess) {
+    kern<<<(int)grid, 32, smem, stream>>>(a, p, sp, queue, stats, jscratch, cell_doubles);
+    e = cudaGetLastError();
+  }
+  const cudaError_t e2 = cudaFreeAsync(jscratch, stream);
+  return e != cudaSuccess ? e : e2;
+}
+#endif // PRX_HAVE_COOP
 
 // =====================================================================================
 // probes (parity tests of the device thermo-chemistry)
@@ -766,6 +1302,8 @@ cudaError_t launch_rk64(const BoxArgs& a, const prx_config& cfg, int* queue, Dev
   return cudaGetLastError();
 }
 
+int effective_bdf_variant(const SchedParams& sp);
+
 cudaError_t launch_bdf(
   const BoxArgs& a, const prx_config& cfg, const double* typ_vals, int* queue, DevStats* stats,
   const SchedParams& sp, cudaStream_t stream)
@@ -789,16 +1327,31 @@ cudaError_t launch_bdf(
   p.array4_semantics = (a.layout == LAYOUT_ARRAY4);
   // kernel generation: 1 = shared-memory columns incl. the Newton matrix, 2 = columns, matrix thread-local,
   // 0 = first generation (thread-local state, straight-line chemistry); default per mechanism
-  int variant = sp.bdf_variant;
-  if (variant < 0) {
-    variant = PRX_BDF_DEFAULT_VARIANT;
+  const int variant = effective_bdf_variant(sp);
+#if PRX_HAVE_COOP
+  switch (variant) { // G lanes per cell
+  case 8:
+    return launch_bdfc<8>(a, p, sp, queue, stats, stream);
+  case 16:
+    return launch_bdfc<16>(a, p, sp, queue, stats, stream);
+  case 32:
+    return launch_bdfc<32>(a, p, sp, queue, stats, stream);
+  default:
+    break;
   }
+#endif
 #if PRX_HAVE_BDF2
   if (variant == 1) {
     return launch_bdf2<true>(a, p, sp, queue, stats, stream);
   }
   if (variant == 2) {
     return launch_bdf2<false>(a, p, sp, queue, stats, stream);
+  }
+  if (variant == 3) {
+    return launch_bdf3<false>(a, p, sp, queue, stats, stream);
+  }
+  if (variant == 4) {
+    return launch_bdf3<true>(a, p, sp, queue, stats, stream);
   }
 #endif
   auto kern = PRX_CAT(bdf_kernel_, PRX_MECH_SUFFIX);
@@ -809,6 +1362,45 @@ cudaError_t launch_bdf(
   }
   kern<<<grid, PRX_BLOCK, 0, stream>>>(a, p, sp, queue, stats);
   return cudaGetLastError();
+}
+
+#define PRX_STR2(x) #x
+#define PRX_STR(x) PRX_STR2(x)
+int effective_bdf_variant(const SchedParams& sp)
+{
+  int v = sp.bdf_variant < 0 ? PRX_BDF_DEFAULT_VARIANT : sp.bdf_variant;
+#if !PRX_HAVE_COOP
+  if (v >= 8) {
+    v = 0;
+  }
+#endif
+#if !PRX_HAVE_BDF2
+  if (v >= 1 && v <= 4) {
+    v = 0;
+  }
+#endif
+  return v;
+}
+
+const char* kernel_name(int reactor_kind, const SchedParams& sp)
+{
+  if (reactor_kind == PRX_REACTOR_RK64) {
+    return "rk64_kernel_" PRX_STR(PRX_MECH_SUFFIX);
+  }
+  switch (effective_bdf_variant(sp)) {
+  case 8:
+  case 16:
+  case 32:
+    return "bdfc_kernel_" PRX_STR(PRX_MECH_SUFFIX);
+  case 1:
+  case 2:
+    return "bdf2_kernel_" PRX_STR(PRX_MECH_SUFFIX);
+  case 3:
+  case 4:
+    return "bdf3_kernel_" PRX_STR(PRX_MECH_SUFFIX);
+  default:
+    return "bdf_kernel_" PRX_STR(PRX_MECH_SUFFIX);
+  }
 }
 
 cudaError_t probe_rhs(
@@ -834,7 +1426,7 @@ cudaError_t probe_jac(int n, int reactor_type, const double* y, double* J, cudaS
   return e;
 }
 
-const MechOps g_ops = {PRX_NUM_SPECIES, PRX_NUM_REACTIONS, PRX_MECH_NAME, prx_species_names, launch_rk64, launch_bdf, probe_rhs, probe_jac,
+const MechOps g_ops = {PRX_NUM_SPECIES, PRX_NUM_REACTIONS, PRX_MECH_NAME, prx_species_names, launch_rk64, launch_bdf, kernel_name, probe_rhs, probe_jac,
                        launch_flatten, launch_unflatten};
 
 } // namespace

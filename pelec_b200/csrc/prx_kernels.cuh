@@ -71,6 +71,7 @@ struct MechOps
   cudaError_t (*launch_bdf)(
     const BoxArgs&, const prx_config&, const double* typ_vals_host, int* queue, DevStats* stats,
     const SchedParams&, cudaStream_t stream);
+  const char* (*kernel_name)(int reactor_kind, const SchedParams&);
   cudaError_t (*probe_rhs)(
     int n, double t, int reactor_type, const double* y, const double* rhoe, const double* rhoesrc,
     const double* rYsrc, double* ydot, cudaStream_t stream);

@@ -289,6 +289,346 @@ PRX_DEV double reaction_q(const int r, const RxCommon& c, CV sc, GV g)
   return qf - qr;
 }
 
+// =====================================================================================
+// Table-driven analytic Jacobian (aJacobian, e.g. LiDryer mechanism.H:3905-5138 + DWDOT :5141-5162):
+// the same per-reaction derivation the generator writes out as straight-line code (gen.py emit_ajacobian),
+// evaluated from the tables.  reaction_jac is shared by the serial form below (host-tested bit-for-bit
+// against the generated ajacobian) and by the cooperative form (prx_coop.cuh jac_coop).
+// =====================================================================================
+struct JacCommon
+{
+  double T, invT, invT2, logT, refC, refCinv, mixture;
+};
+PRX_DEV JacCommon jac_common(const double T, const double mixture)
+{
+  JacCommon c;
+  c.T = T;
+  c.invT = 1.0 / T;
+  c.invT2 = c.invT * c.invT;
+  c.logT = log(T);
+  c.refC = PRX_REFC_NUM / PRX_REFC_DEN / T;
+  c.refCinv = 1.0 / c.refC;
+  c.mixture = mixture;
+  return c;
+}
+
+struct RxJac
+{
+  double q, dqdT, kf, kr, dcdc; // kf/kr already carry the third-body / falloff correction
+};
+
+template <class TB, class CV, class GV, class HV>
+PRX_DEV RxJac reaction_jac(const int r, const JacCommon& c, CV sc, GV g, HV h)
+{
+  const int m = TB::meta(r);
+  RxJac o;
+  double phi_f = sc[TB::reac(3 * r)];
+  const int nr = rx_nreac(m);
+  if (nr > 1) {
+    phi_f = phi_f * sc[TB::reac(3 * r + 1)];
+  }
+  if (nr > 2) {
+    phi_f = phi_f * sc[TB::reac(3 * r + 2)];
+  }
+  double k_f = TB::A(r);
+  if (!rx_noexp(m)) {
+    k_f = k_f * exp(TB::beta(r) * c.logT - TB::Ea(r) * c.invT);
+  }
+  const double dlnkfdT = TB::beta(r) * c.invT + TB::Ea(r) * c.invT2;
+  double phi_r = 0.0, k_r = 0.0, dkrdT = 0.0;
+  if (rx_rev(m)) {
+    phi_r = sc[TB::prod(3 * r)];
+    const int np = rx_nprod(m);
+    if (np > 1) {
+      phi_r = phi_r * sc[TB::prod(3 * r + 1)];
+    }
+    if (np > 2) {
+      phi_r = phi_r * sc[TB::prod(3 * r + 2)];
+    }
+    const int ng = rx_ng(m);
+    double dG = (double)TB::gcoef(6 * r) * g[TB::gidx(6 * r)];
+    double dH = (double)TB::gcoef(6 * r) * h[TB::gidx(6 * r)];
+    for (int j = 1; j < ng; j++) {
+      dG = dG + (double)TB::gcoef(6 * r + j) * g[TB::gidx(6 * r + j)];
+      dH = dH + (double)TB::gcoef(6 * r + j) * h[TB::gidx(6 * r + j)];
+    }
+    double Kinv = exp(-(dG));
+    const int rc = rx_refc(m);
+    if (rc == 1) {
+      Kinv = c.refC * Kinv;
+    } else if (rc == -1) {
+      Kinv = c.refCinv * Kinv;
+    } else if (rc == 2) {
+      Kinv = (c.refC * c.refC) * Kinv;
+    } else if (rc == -2) {
+      Kinv = (c.refCinv * c.refCinv) * Kinv;
+    }
+    k_r = k_f * Kinv;
+    const double dlnKinvdT = c.invT * ((dH) - (double)rc);
+    dkrdT = (dlnkfdT + dlnKinvdT) * k_r;
+  }
+  const double q_nocor = k_f * phi_f - k_r * phi_r;
+  const int typ = rx_type(m);
+  if (typ == 0) {
+    o.q = q_nocor;
+    o.dqdT = dlnkfdT * k_f * phi_f - dkrdT * phi_r;
+    o.dcdc = 0.0;
+  } else {
+    const int tb = TB::tb_of(r);
+    double alpha = c.mixture;
+    for (int j = TB::eff_ptr(tb); j < TB::eff_ptr(tb + 1); j++) {
+      alpha = alpha + TB::eff_val(j) * sc[TB::eff_idx(j)];
+    }
+    if (typ == 1) {
+      o.q = alpha * q_nocor;
+      o.dqdT = alpha * (dlnkfdT * k_f * phi_f - dkrdT * phi_r);
+      o.dcdc = q_nocor;
+      k_f *= alpha;
+      k_r *= alpha;
+    } else {
+      const int f = TB::fo_of(r);
+      const double ln10 = PRX_LN10;
+      const double log10e = 1.0 / PRX_LN10;
+      const double k_0 = TB::lowA(f) * exp(TB::lowb(f) * c.logT - TB::lowE(f) * c.invT);
+      const double Pr = alpha / k_f * k_0;
+      const double fPr = Pr / (1.0 + Pr);
+      const double dlnk0dT = TB::lowb(f) * c.invT + TB::lowE(f) * c.invT2;
+      const double dlogPrdT = log10e * (dlnk0dT - dlnkfdT);
+      const double dlogfPrdT = dlogPrdT / (1.0 + Pr);
+      double F = 1.0, dlogFdlogPr = 0.0, dlogFdT = 0.0;
+      if (typ == 2) {
+        const int fl = TB::fo_flags(f);
+        const int nt = fl & 3;
+        const double logPr = log10(Pr);
+        const double Fc0 = (TB::fc_a(2 * f)) * exp(-c.T * TB::fc_x(2 * f));
+        double Fcent = Fc0;
+        double dsum = -Fc0 * TB::fc_x(2 * f);
+        if (nt > 1) {
+          const double Fc1 = (TB::fc_a(2 * f + 1)) * exp(-c.T * TB::fc_x(2 * f + 1));
+          Fcent = Fcent + Fc1;
+          dsum = dsum + (-Fc1 * TB::fc_x(2 * f + 1));
+        }
+        if (fl & 4) {
+          const double FcT = exp(TB::fc_invT(f) * c.invT);
+          Fcent = Fcent + FcT;
+          dsum = dsum + (-FcT * (TB::fc_invT(f)) * c.invT2);
+        }
+        Fcent = Fcent + TB::fc_const(f);
+        const double logFcent = log10(Fcent);
+        const double troe_c = -0.4 - 0.67 * logFcent;
+        const double troe_n = 0.75 - 1.27 * logFcent;
+        const double troePr_den = 1.0 / (troe_n - 0.14 * (troe_c + logPr));
+        const double troePr = (troe_c + logPr) * troePr_den;
+        const double troe = 1.0 / (1.0 + troePr * troePr);
+        F = exp(ln10 * logFcent * troe);
+        const double dlogFcentdT = log10e / Fcent * (dsum);
+        const double dlogFdcn_fac = 2.0 * logFcent * troe * troe * troePr * troePr_den;
+        const double dlogFdc = -troe_n * dlogFdcn_fac * troePr_den;
+        const double dlogFdn = dlogFdcn_fac * troePr;
+        dlogFdlogPr = dlogFdc;
+        dlogFdT = dlogFcentdT * (troe - 0.67 * dlogFdc - 1.27 * dlogFdn) + dlogFdlogPr * dlogPrdT;
+      }
+      const double Corr = fPr * F;
+      o.q = Corr * q_nocor;
+      const double dlnCorrdT = ln10 * (dlogfPrdT + dlogFdT);
+      o.dqdT = Corr * (dlnkfdT * k_f * phi_f - dkrdT * phi_r) + dlnCorrdT * o.q;
+      o.dcdc = o.q / alpha * (1.0 / (Pr + 1.0) + dlogFdlogPr);
+      k_f *= Corr;
+      k_r *= Corr;
+    }
+  }
+  o.kf = k_f;
+  o.kr = k_r;
+  return o;
+}
+
+// one "direct" term n * k * sc[o1] * sc[o2] (packed n | o1 << 8 | o2 << 16, 255 = no factor)
+template <class CV>
+PRX_DEV double direct_term(const int packed, const double k, CV sc)
+{
+  const int n = packed & 255, o1 = (packed >> 8) & 255, o2 = (packed >> 16) & 255;
+  double t = (n > 1) ? (double)n * k : k;
+  if (o1 != 255) {
+    t = t * sc[o1];
+  }
+  if (o2 != 255) {
+    t = t * sc[o2];
+  }
+  return t;
+}
+// dq/dC of direct species d of reaction r: [+ forward term] [- reverse term]
+template <class TB, class CV>
+PRX_DEV double direct_dqdc(const int r, const int d, const RxJac& x, CV sc)
+{
+  const int pf = TB::jd_f(6 * r + d), pr = TB::jd_r(6 * r + d);
+  double v = 0.0;
+  if (pf != 0) {
+    v = direct_term(pf, x.kf, sc);
+    if (pr != 0) {
+      v = v - direct_term(pr, x.kr, sc);
+    }
+  } else {
+    v = -direct_term(pr, x.kr, sc);
+  }
+  return v;
+}
+
+// Serial form (one thread): J column-major NEQ x NEQ, PRX_J(row, col) = J[col*NEQ + row]; sc = SI
+// concentrations; scratch vectors g, h, wdot, dqdc of N doubles each.
+template <class TB>
+PRX_DEV void ajacobian_tab(double* J, const double* sc, const double T, const int consP, double* g, double* h,
+                           double* wdot, double* dqdc)
+{
+  for (int i = 0; i < NEQ * NEQ; i++) {
+    J[i] = 0.0;
+  }
+  double mixture = 0.0;
+  for (int k = 0; k < N; k++) {
+    wdot[k] = 0.0;
+    dqdc[k] = 0.0;
+    mixture += sc[k];
+  }
+  const JacCommon c = jac_common(T, mixture);
+  TPow p = tpow_poly(T);
+  p.logT = c.logT;
+  for (int k = 0; k < N; k++) {
+    g[k] = sp_gibbs<TB>(k, p);
+    h[k] = sp_h_RT<TB>(k, p);
+  }
+  for (int r = 0; r < PRX_NUM_REACTIONS; r++) {
+    const RxJac x = reaction_jac<TB>(r, c, sc, g, h);
+    const int jm = TB::jmeta(r);
+    const int nnu = jm & 15, nd = (jm >> 4) & 15;
+    for (int j = 0; j < nnu; j++) {
+      wdot[TB::jnu_idx(5 * r + j)] += ((double)TB::jnu_c(5 * r + j)) * x.q;
+    }
+    const int typ = rx_type(TB::meta(r));
+    if (typ == 0) {
+      for (int d = 0; d < nd; d++) {
+        const int k = TB::jd_k(6 * r + d);
+        const double v = direct_dqdc<TB>(r, d, x, sc);
+        for (int j = 0; j < nnu; j++) {
+          J[k * NEQ + TB::jnu_idx(5 * r + j)] += ((double)TB::jnu_c(5 * r + j)) * v;
+        }
+      }
+    } else {
+      const int tb = TB::tb_of(r);
+      for (int k = 0; k < N; k++) {
+        int d = -1;
+        for (int dd = 0; dd < nd; dd++) {
+          if (TB::jd_k(6 * r + dd) == k) {
+            d = dd;
+          }
+        }
+        if (consP) {
+          if (d < 0 && !TB::tb_has(tb * N + k)) {
+            continue;
+          }
+          double v;
+          if (TB::tb_has(tb * N + k)) {
+            v = (TB::tb_eff(tb * N + k)) * x.dcdc;
+            if (d >= 0) {
+              const int pf = TB::jd_f(6 * r + d), pr = TB::jd_r(6 * r + d);
+              if (pf != 0) {
+                v = v + direct_term(pf, x.kf, sc);
+              }
+              if (pr != 0) {
+                v = v - direct_term(pr, x.kr, sc);
+              }
+            }
+          } else {
+            v = direct_dqdc<TB>(r, d, x, sc);
+          }
+          for (int j = 0; j < nnu; j++) {
+            J[k * NEQ + TB::jnu_idx(5 * r + j)] += ((double)TB::jnu_c(5 * r + j)) * v;
+          }
+        } else {
+          // reference quirk (gen.py emit_ajacobian): dqdc[k] keeps its value from an earlier reaction when
+          // 1 + eff_k == 0 and k has no direct term
+          const double tot = TB::tb_tot(tb * N + k);
+          if (tot != 0.0) {
+            double v = (tot == 1.0) ? x.dcdc : (tot)*x.dcdc;
+            if (d >= 0) {
+              const int pf = TB::jd_f(6 * r + d), pr = TB::jd_r(6 * r + d);
+              if (pf != 0) {
+                v = v + direct_term(pf, x.kf, sc);
+              }
+              if (pr != 0) {
+                v = v - direct_term(pr, x.kr, sc);
+              }
+            }
+            dqdc[k] = v;
+          } else if (d >= 0) {
+            dqdc[k] = direct_dqdc<TB>(r, d, x, sc);
+          }
+        }
+      }
+      if (!consP) {
+        for (int k = 0; k < N; k++) {
+          for (int j = 0; j < nnu; j++) {
+            J[k * NEQ + TB::jnu_idx(5 * r + j)] += ((double)TB::jnu_c(5 * r + j)) * dqdc[k];
+          }
+        }
+      }
+    }
+    for (int j = 0; j < nnu; j++) {
+      J[N * NEQ + TB::jnu_idx(5 * r + j)] += ((double)TB::jnu_c(5 * r + j)) * x.dqdT;
+    }
+  }
+  // temperature row (g is reused for c_R, dqdc for dcRdT, h becomes eh_RT)
+  double cmix = 0.0, ehmix = 0.0, dcmixdT = 0.0, dehmixdT = 0.0;
+  for (int k = 0; k < N; k++) {
+    const double c_R = consP ? sp_cp_R<TB>(k, p) : sp_cv_R<TB>(k, p);
+    const double eh = consP ? h[k] : sp_e_RT<TB>(k, p);
+    const double dcR = sp_dcvpRdT<TB>(k, p);
+    g[k] = c_R;
+    h[k] = eh;
+    cmix += c_R * sc[k];
+    dcmixdT += dcR * sc[k];
+    ehmix += eh * wdot[k];
+    dehmixdT += c.invT * (c_R - eh) * wdot[k] + eh * J[N * NEQ + k];
+  }
+  const double cmixinv = 1.0 / cmix;
+  const double tmp1 = ehmix * cmixinv;
+  const double tmp3 = cmixinv * T;
+  const double tmp2 = tmp1 * tmp3;
+  for (int k = 0; k < N; k++) {
+    double dehmixdc = 0.0;
+    for (int mm = 0; mm < N; mm++) {
+      dehmixdc += h[mm] * J[k * NEQ + mm];
+    }
+    J[k * NEQ + N] = tmp2 * g[k] - tmp3 * dehmixdc;
+  }
+  J[N * NEQ + N] = -tmp1 + tmp2 * dcmixdT - tmp3 * dehmixdT;
+}
+
+// jac_analytic (prx_chem.cuh) with the table-driven aJacobian: serial form used by the host tests
+template <class TB, class Store>
+PRX_DEV void jac_analytic_tab(const int reactor_type, const double* ydata, double* Jt, Store&& JM)
+{
+  double rho = 0.0;
+  for (int i = 0; i < N; i++) {
+    rho = rho + ydata[i];
+  }
+  const double temp = ydata[N];
+  double c[N], g[N], h[N], wdot[N], dqdc[N];
+  for (int i = 0; i < N; i++) {
+    const double Yi = ydata[i] / rho;
+    c[i] = 1.e6 * (rho * Yi * TB::imw(i));
+  }
+  ajacobian_tab<TB>(Jt, c, temp, reactor_type == 2, g, h, wdot, dqdc);
+  for (int i = 0; i < N; i++) {
+    for (int k = 0; k < N; k++) {
+      JM(k, i, Jt[i * NEQ + k] * TB::mw(k) * TB::imw(i));
+    }
+    JM(N, i, (Jt[i * NEQ + N] * 1.e6) * TB::imw(i));
+  }
+  for (int i = 0; i < N; i++) {
+    JM(i, N, (Jt[N * NEQ + i] * 1.e-6) * TB::mw(i));
+  }
+  JM(N, N, Jt[N * NEQ + N]);
+}
+
 // per-cell constants of the ODE that do not fit in registers stay in HBM/L2: the external species
 // source is re-read through this accessor at every RHS (N coalesced loads, L2-resident)
 struct SrcScalars

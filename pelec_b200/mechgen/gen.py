@@ -615,6 +615,57 @@ class Emitter:
                         sp_c.append(lit(c))
             sp_ptr.append(len(sp_r))
         arrays += [("short", "sp_ptr", [str(x) for x in sp_ptr]), ("short", "sp_r", sp_r), ("float", "sp_c", sp_c)]
+        # ---- Jacobian tables (prx_tchem.cuh ajacobian_tab / prx_coop.cuh jac_coop; same structure as emit_ajacobian)
+        # jnu: merged stoichiometric rows sorted by species; jd: "direct" dq/dC terms per distinct species
+        # (forward term n*k_f*others, reverse term n*k_r*others, packed n | o1 << 8 | o2 << 16, 255 = none);
+        # tb_tot / tb_eff / tb_has: dense third-body efficiency rows (1 + eff, eff, eff present)
+        jmeta, jnu_idx, jnu_c, jd_k, jd_f, jd_r = [], [], [], [], [], []
+        tb_tot, tb_eff, tb_has = [], [], []
+
+        def powers(lst):
+            pw = {}
+            for i in lst:
+                pw[i] = pw.get(i, 0) + 1
+            return pw
+
+        def pack(pw, k):
+            others = []
+            for i, m in pw.items():
+                others += [i] * (m - 1 if i == k else m)
+            assert len(others) <= 2
+            others += [255] * (2 - len(others))
+            return pw[k] | (others[0] << 8) | (others[1] << 16)
+
+        for r in R:
+            nu = {}
+            for k, c in r["wdot"]:
+                nu[k] = nu.get(k, 0.0) + float(c)
+            rows = sorted(nu.items())
+            pf = powers(r["reactants"])
+            pr = powers(r["products"]) if r["reversible"] else {}
+            ks = sorted(set(pf) | set(pr))
+            assert len(rows) <= 5 and len(ks) <= 6
+            jmeta.append(len(rows) | (len(ks) << 4))
+            jnu_idx += [str(k) for k, c in rows] + ["0"] * (5 - len(rows))
+            jnu_c += [repr(c) for k, c in rows] + ["0.0"] * (5 - len(rows))
+            jd_k += [str(k) for k in ks] + ["0"] * (6 - len(ks))
+            jd_f += [str(pack(pf, k)) if k in pf else "0" for k in ks] + ["0"] * (6 - len(ks))
+            jd_r += [str(pack(pr, k)) if k in pr else "0" for k in ks] + ["0"] * (6 - len(ks))
+            if r["type"] != "elementary":
+                eff = {}
+                for i, c in r["eff"]:
+                    eff[i] = eff.get(i, 0.0) + float(c)
+                tb_tot += [repr(1.0 + eff.get(k, 0.0)) for k in range(N)]
+                tb_eff += [repr(eff.get(k, 0.0)) for k in range(N)]
+                tb_has += ["1" if k in eff else "0" for k in range(N)]
+        for c in jnu_c:
+            import struct
+            assert struct.unpack("f", struct.pack("f", float(c)))[0] == float(c), c
+        n_common = len(arrays)  # everything after this index is emitted in global space only (64 KB constant bank)
+        arrays += [("short", "jmeta", [str(x) for x in jmeta]), ("unsigned char", "jnu_idx", jnu_idx), ("float", "jnu_c", jnu_c),
+                   ("unsigned char", "jd_k", jd_k), ("int", "jd_f", jd_f), ("int", "jd_r", jd_r),
+                   ("double", "tb_tot", tb_tot or ["0.0"]), ("double", "tb_eff", tb_eff or ["0.0"]),
+                   ("unsigned char", "tb_has", tb_has or ["0"])]
         for c in gcoef + wcoef + sp_c:  # stoichiometric coefficients must be exact in float
             import struct
             assert struct.unpack("f", struct.pack("f", float(c)))[0] == float(c), c
@@ -637,12 +688,12 @@ class Emitter:
             w("#define PRX_TABC static const")
             w("#define PRX_TABG static const")
         for space, pre in (("PRX_TABC", "tc_"), ("PRX_TABG", "tg_")):
-            for ct, nm, vals in arrays:
+            for ct, nm, vals in (arrays[:n_common] if pre == "tc_" else arrays):
                 w("%s %s %s%s[%d] = {%s};" % (space, ct, pre, nm, len(vals), ", ".join(vals)))
         if self.fl == "cuda":
             for sname, pre in (("TabC", "tc_"), ("TabG", "tg_")):
                 w("struct %s {" % sname)
-                for ct, nm, vals in arrays:
+                for ct, nm, vals in (arrays[:n_common] if pre == "tc_" else arrays):
                     w("  PRX_TABFN %s %s(const int i) { return %s%s[i]; }" % (ct, nm, pre, nm))
                 w("};")
         w()

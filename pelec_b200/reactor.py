@@ -93,6 +93,8 @@ def load_library():
     L.prx_reset_stats.argtypes = [vp]
     L.prx_get_stats.argtypes = [vp, C.POINTER(prx_stats)]
     L.prx_last_react_return.argtypes = [vp]
+    L.prx_kernel_name.argtypes = [vp]
+    L.prx_kernel_name.restype = C.c_char_p
     L.prx_probe_rhs_host.argtypes = [vp, C.c_int, C.c_double, vp, vp, vp, vp, vp]
     L.prx_probe_jac_host.argtypes = [vp, C.c_int, vp, vp]
     _lib = L
@@ -290,6 +292,9 @@ class ReactorB200:
 
     def reset_stats(self):
         self._check(self.lib.prx_reset_stats(self.h))
+
+    def kernel_name(self):
+        return self.lib.prx_kernel_name(self.h).decode()
 
     def last_react_return(self):
         return self.lib.prx_last_react_return(self.h)

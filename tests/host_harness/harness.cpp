@@ -185,6 +185,23 @@ int hh_rhs(int tab, int n, double t, int reactor_type, const double* y, const do
   return 0;
 }
 
+// analytic Jacobian of n states (state-major y, J[s][col][row]): generated straight-line (tab = 0) or
+// table-driven (tab = 1) aJacobian
+int hh_jac(int tab, int n, int reactor_type, const double* y, double* J)
+{
+  static double Jt[NEQ * NEQ];
+  for (int s = 0; s < n; s++) {
+    double* Jo = J + (size_t)s * NEQ * NEQ;
+    auto st = [Jo](int row, int col, double v) { Jo[col * NEQ + row] = v; };
+    if (tab) {
+      jac_analytic_tab<TabG>(reactor_type, y + s * NEQ, Jt, st);
+    } else {
+      jac_analytic(reactor_type, y + s * NEQ, Jt, st);
+    }
+  }
+  return 0;
+}
+
 int hh_react_rk64_variant(
   int tab, int reactor_type, double atol, int nsg, int nsmin, int nsmax, int ncells, double* rY,
   const double* rYsrc, double* T, double* rE, const double* rEsrc, double* FC, double dt, double time)
