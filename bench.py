@@ -309,7 +309,8 @@ def run_b200(a):
             "gpu_launches": a.steps,
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
-                "frac": achieved / peak.value if peak.value > 0 else None, "traffic": None,
+                "frac": achieved / peak.value if peak.value > 0 else None,
+                "traffic": ncu_traffic(r.kernel_name(), ncell),
                 "peak_source": "measured in this run: register-resident DFMA chains (prx_measure_fp64_peak)",
                 "kernel": r.kernel_name(),
                 "kernel_ms": kms, "flops_per_launch": flops_per_launch,
@@ -328,6 +329,18 @@ def run_b200(a):
     r.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(kernel, ncell):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed ncu capture
+    (profiles/ncu_traffic.json: bytes per cell measured on a 64^3 launch, scaled to this launch's cell count;
+    the state of a cell never depends on the box size).  None when no capture of that kernel is committed."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]
+        return {"dram_bytes": t["dram_bytes_per_cell"] * ncell, "dram_bytes_per_cell": t["dram_bytes_per_cell"],
+                "source": t["source"]}
+    except Exception:
+        return None
 
 
 def synth_states(mech, n):

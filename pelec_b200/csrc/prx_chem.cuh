@@ -32,6 +32,15 @@
 #define PRX_HD __host__ __device__ __forceinline__
 #endif
 
+#if defined(PRX_NOINLINE_MATH) && !defined(PRX_HOST_TEST)
+// out-of-line transcendentals for the generated straight-line code (see gen.py): one copy of each libm
+// expansion per kernel instead of one per call site
+static __device__ __noinline__ double prx_exp(const double x) { return exp(x); }
+static __device__ __noinline__ double prx_log(const double x) { return log(x); }
+static __device__ __noinline__ double prx_log10(const double x) { return log10(x); }
+#define PRX_MATH_REDIRECT 1
+#endif
+
 #include PRX_MECH_HEADER
 
 #define PRX_N PRX_NUM_SPECIES

@@ -70,11 +70,14 @@ struct BdfStoreCoop
   typedef double* Mat;
   Grp<G> g;
   double* base;
-  double* gJ;
+  double* gJ; // savedJ slot (global)
+  double* gA; // Newton matrix slot in global memory, or nullptr: the matrix is in the shared-memory block
   int nz;
-  __host__ __device__ static int doubles_per_cell(const int qmax)
+  // a_global: large systems (dodecane_lu: 23 KB per matrix) keep the Newton matrix in a global (L2 resident)
+  // slot instead, which quadruples the number of resident warps; its accesses are coalesced column segments
+  __host__ __device__ static int doubles_per_cell(const int qmax, const bool a_global)
   {
-    int d = (qmax + 1 + 6) * NEQ + 3 * N + PRX_NUM_REACTIONS + NEQ * NEQ + (NEQ + 1) / 2;
+    int d = (qmax + 1 + 6) * NEQ + 3 * N + PRX_NUM_REACTIONS + (NEQ + 1) / 2 + (a_global ? 0 : NEQ * NEQ);
     if (G < 32) { // cells of one warp start 8 doubles apart modulo 16: their G-wide rows use distinct banks
       while ((d & 15) != 8) {
         d++;
@@ -94,8 +97,8 @@ struct BdfStoreCoop
   PRX_MEM double* gs() const { return sc() + N; }
   PRX_MEM double* dq() const { return gs() + N; }
   PRX_MEM double* qv() const { return dq() + N; }
-  PRX_MEM Mat A() const { return qv() + PRX_NUM_REACTIONS; }
-  PRX_MEM int* piv() const { return reinterpret_cast<int*>(A() + NEQ * NEQ); }
+  PRX_MEM int* piv() const { return reinterpret_cast<int*>(qv() + PRX_NUM_REACTIONS); }
+  PRX_MEM Mat A() const { return gA != nullptr ? gA : (qv() + PRX_NUM_REACTIONS + (NEQ + 1) / 2); }
   PRX_MEM double* savedJ() const { return gJ; }
   // cooperative hooks
   PRX_MEM int vbegin() const { return g.gl; }

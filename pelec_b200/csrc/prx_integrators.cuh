@@ -39,7 +39,9 @@
 #define PRX_VLOOP
 #define PRX_MLOOP
 #define PRX_ILOOP
+#define PRX_UNROLL
 #else
+#define PRX_UNROLL _Pragma("unroll")
 #define PRX_VLOOP _Pragma("unroll 1") // per-component vector loops
 #define PRX_MLOOP _Pragma("unroll 1") // column loops of the dense matrix code
 #define PRX_ILOOP _Pragma("unroll 2") // innermost row loops of the dense matrix code
@@ -678,15 +680,237 @@ PRX_DEV void dense_getrs(MA a, const int* p, VB b)
   b[0] /= a[0];
 }
 
+// Device forms of GETRF / GETRS for small systems, one thread per matrix, the matrix in (L2-backed) memory.
+// ncu (profiles/r01d_*): with rolled loops every a[...] access of the elimination was a dependent memory round
+// trip (long-scoreboard stalls = 45-49 % of all samples, concentrated here).  These forms do the same
+// per-entry arithmetic in the same order, but with compile-time row/column offsets and all loads of a step
+// issued before its stores, so the accesses of one elimination step are in flight together.
+template <class MA>
+PRX_DEV int dense_getrf_small(MA a, int* p)
+{
+  PRX_MLOOP
+  for (int k = 0; k < NEQ; k++) {
+    const int ck = k * NEQ;
+    double col[NEQ];
+PRX_UNROLL
+    for (int i = 0; i < NEQ; i++) {
+      col[i] = (i >= k) ? a[ck + i] : 0.0;
+    }
+    int l = k;
+    double best = -1.0, pv = 0.0, akk = 0.0;
+PRX_UNROLL
+    for (int i = 0; i < NEQ; i++) {
+      if (i >= k) {
+        const double v = fabs(col[i]);
+        if (i == k) {
+          akk = col[i];
+          pv = col[i];
+          best = v;
+        } else if (v > best) {
+          best = v;
+          l = i;
+          pv = col[i];
+        }
+      }
+    }
+    p[k] = l;
+    if (pv == 0.0) {
+      return k + 1;
+    }
+    double rk[NEQ]; // row k of every column after the interchange
+PRX_UNROLL
+    for (int j = 0; j < NEQ; j++) {
+      rk[j] = a[j * NEQ + l];
+    }
+    if (l != k) {
+      double t[NEQ];
+PRX_UNROLL
+      for (int j = 0; j < NEQ; j++) {
+        t[j] = a[j * NEQ + k];
+      }
+PRX_UNROLL
+      for (int j = 0; j < NEQ; j++) {
+        a[j * NEQ + l] = t[j];
+        a[j * NEQ + k] = rk[j];
+      }
+    }
+    const double mult = 1.0 / pv;
+    double m[NEQ];
+PRX_UNROLL
+    for (int i = 0; i < NEQ; i++) {
+      const double ci = (i == l) ? akk : col[i]; // column k below the diagonal, after the interchange
+      m[i] = ci * mult;
+      if (i > k) {
+        a[ck + i] = m[i];
+      }
+    }
+PRX_UNROLL
+    for (int j = 0; j < NEQ; j++) {
+      if (j > k) {
+        const double a_kj = rk[j];
+        double x[NEQ];
+PRX_UNROLL
+        for (int i = 0; i < NEQ; i++) {
+          x[i] = (i > k) ? a[j * NEQ + i] : 0.0;
+        }
+        if (a_kj != 0.0) {
+PRX_UNROLL
+          for (int i = 0; i < NEQ; i++) {
+            if (i > k) {
+              a[j * NEQ + i] = x[i] - a_kj * m[i];
+            }
+          }
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+// Same, for mid-size systems (NEQ <= 24): the column loop stays rolled (one memory round trip per column
+// instead of one per entry), rows are compile-time offsets; row interchanges in chunks of 8 columns.
+template <class MA>
+PRX_DEV int dense_getrf_mid(MA a, int* p)
+{
+  PRX_MLOOP
+  for (int k = 0; k < NEQ; k++) {
+    const int ck = k * NEQ;
+    double m[NEQ];
+    int l = k;
+    double best = -1.0, pv = 0.0, akk = 0.0;
+    PRX_UNROLL
+    for (int i = 0; i < NEQ; i++) {
+      m[i] = (i >= k) ? a[ck + i] : 0.0;
+    }
+    PRX_UNROLL
+    for (int i = 0; i < NEQ; i++) {
+      if (i >= k) {
+        const double v = fabs(m[i]);
+        if (i == k) {
+          akk = m[i];
+          pv = m[i];
+          best = v;
+        } else if (v > best) {
+          best = v;
+          l = i;
+          pv = m[i];
+        }
+      }
+    }
+    p[k] = l;
+    if (pv == 0.0) {
+      return k + 1;
+    }
+    if (l != k) {
+      PRX_MLOOP
+      for (int j0 = 0; j0 < NEQ; j0 += 8) {
+        double tl[8], tk[8];
+        PRX_UNROLL
+        for (int jj = 0; jj < 8; jj++) {
+          const int j = (j0 + jj < NEQ) ? j0 + jj : NEQ - 1;
+          tl[jj] = a[j * NEQ + l];
+          tk[jj] = a[j * NEQ + k];
+        }
+        PRX_UNROLL
+        for (int jj = 0; jj < 8; jj++) {
+          if (j0 + jj < NEQ) {
+            a[(j0 + jj) * NEQ + l] = tk[jj];
+            a[(j0 + jj) * NEQ + k] = tl[jj];
+          }
+        }
+      }
+    }
+    const double mult = 1.0 / pv;
+    PRX_UNROLL
+    for (int i = 0; i < NEQ; i++) {
+      const double ci = (i == l) ? akk : m[i];
+      m[i] = ci * mult;
+      if (i > k) {
+        a[ck + i] = m[i];
+      }
+    }
+    PRX_MLOOP
+    for (int j = k + 1; j < NEQ; j++) {
+      const int cj = j * NEQ;
+      const double a_kj = a[cj + k];
+      double x[NEQ];
+      PRX_UNROLL
+      for (int i = 0; i < NEQ; i++) {
+        x[i] = (i > k) ? a[cj + i] : 0.0;
+      }
+      if (a_kj != 0.0) {
+        PRX_UNROLL
+        for (int i = 0; i < NEQ; i++) {
+          if (i > k) {
+            a[cj + i] = x[i] - a_kj * m[i];
+          }
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+template <class MA, class VB>
+PRX_DEV void dense_getrs_small(MA a, const int* p, VB b)
+{
+  PRX_MLOOP
+  for (int k = 0; k < NEQ; k++) {
+    const int pk = p[k];
+    if (pk != k) {
+      const double tmp = b[k];
+      b[k] = b[pk];
+      b[pk] = tmp;
+    }
+  }
+  double bb[NEQ];
+PRX_UNROLL
+  for (int i = 0; i < NEQ; i++) {
+    bb[i] = b[i];
+  }
+PRX_UNROLL
+  for (int k = 0; k < NEQ - 1; k++) {
+PRX_UNROLL
+    for (int i = k + 1; i < NEQ; i++) {
+      bb[i] -= a[k * NEQ + i] * bb[k];
+    }
+  }
+PRX_UNROLL
+  for (int k = NEQ - 1; k > 0; k--) {
+    bb[k] /= a[k * NEQ + k];
+PRX_UNROLL
+    for (int i = 0; i < k; i++) {
+      bb[i] -= a[k * NEQ + i] * bb[k];
+    }
+  }
+  bb[0] /= a[0];
+PRX_UNROLL
+  for (int i = 0; i < NEQ; i++) {
+    b[i] = bb[i];
+  }
+}
+
 template <class MA, class VB>
 PRX_MEM void BdfStoreLocal::getrs(MA a, const int* p, VB b)
 {
+#ifndef PRX_HOST_TEST
+  if (NEQ <= 24) {
+    dense_getrs_small(a, p, b);
+    return;
+  }
+#endif
   dense_getrs(a, p, b);
 }
 template <int STRIDE, bool A_SMEM>
 template <class MA, class VB>
 PRX_MEM void BdfStoreSmem<STRIDE, A_SMEM>::getrs(MA a, const int* p, VB b)
 {
+#ifndef PRX_HOST_TEST
+  if (NEQ <= 24) {
+    dense_getrs_small(a, p, b);
+    return;
+  }
+#endif
   dense_getrs(a, p, b);
 }
 
@@ -694,6 +918,12 @@ template <int STRIDE, bool SCRATCH>
 template <class MA, class VB>
 PRX_MEM void BdfStoreHot<STRIDE, SCRATCH>::getrs(MA a, const int* p, VB b)
 {
+#ifndef PRX_HOST_TEST
+  if (NEQ <= 24) {
+    dense_getrs_small(a, p, b);
+    return;
+  }
+#endif
   dense_getrs(a, p, b);
 }
 

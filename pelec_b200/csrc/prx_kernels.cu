@@ -323,7 +323,12 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
         ls.masked++;
       }
     }
-    if (!__syncthreads_or(!(exhausted && (cell < 0)))) { // exit test + phase barrier (see rk64 kernel)
+    // exit test; with sp.block_warps != 1 it is block wide and doubles as the phase barrier (see rk64 kernel)
+    if (sp.block_warps != 1) {
+      if (!__syncthreads_or(!(exhausted && (cell < 0)))) {
+        break;
+      }
+    } else if (!__any_sync(FULL, !(exhausted && (cell < 0)))) {
       break;
     }
     // ---- (2) control ----
@@ -331,7 +336,9 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
       req = bdf_resume(s, p);
     }
     // ---- (3) serve ----
-    __syncthreads(); // re-align the warps after the divergent control code, right before the RHS
+    if (sp.block_warps != 1 && sp.block_warps != 3) {
+      __syncthreads(); // re-align the warps after the divergent control code, right before the RHS
+    }
     const unsigned m_rhs = __ballot_sync(FULL, req == REQ_RHS);
     const unsigned m_jac = __ballot_sync(FULL, req == REQ_JAC);
     const unsigned m_lu = __ballot_sync(FULL, req == REQ_LU);
@@ -350,7 +357,7 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
     }
     if (m_lu && ((__popc(m_lu) >= sp.lu_defer_min_lanes) || (m_rhs == 0))) {
       if (req == REQ_LU) {
-        s.lu_info = dense_getrf(s.A(), s.piv());
+        s.lu_info = (NEQ <= 12) ? dense_getrf_small(s.A(), s.piv()) : ((NEQ <= 24) ? dense_getrf_mid(s.A(), s.piv()) : dense_getrf(s.A(), s.piv()));
         req = REQ_NONE;
       }
     }
@@ -497,7 +504,7 @@ __global__ void __launch_bounds__(32) PRX_CAT(bdf2_kernel_, PRX_MECH_SUFFIX)(
     }
     if (m_lu && ((__popc(m_lu) >= sp.lu_defer_min_lanes) || (m_rhs == 0))) {
       if (req == REQ_LU) {
-        s.lu_info = dense_getrf(s.A(), s.piv());
+        s.lu_info = (NEQ <= 12) ? dense_getrf_small(s.A(), s.piv()) : ((NEQ <= 24) ? dense_getrf_mid(s.A(), s.piv()) : dense_getrf(s.A(), s.piv()));
         req = REQ_NONE;
       }
       __syncwarp();
@@ -605,14 +612,17 @@ cudaError_t launch_bdf2(const BoxArgs& a, const BdfParams& p, const SchedParams&
 #endif
 // hot/cold split (BdfStoreHot); TABRHS: table-driven RHS (rolled) instead of the generated straight-line one
 template <bool TABRHS>
-__global__ void __launch_bounds__(32, PRX_BDF3_MINBLOCKS) PRX_CAT(bdf3_kernel_, PRX_MECH_SUFFIX)(
+__global__ void __launch_bounds__(128, PRX_BDF3_MINBLOCKS / 4) PRX_CAT(bdf3_kernel_, PRX_MECH_SUFFIX)(
   const BoxArgs a, const BdfParams p, const SchedParams sp, int* __restrict__ queue, DevStats* __restrict__ stats,
   double* __restrict__ cold, const int cold_doubles)
 {
   typedef BdfCellT<BdfStoreHot<32, TABRHS>, SrcRef> Cell;
   Cell s;
-  s.hot = prx_dyn_smem + threadIdx.x;
-  s.cold = cold + (size_t)blockIdx.x * 32 * cold_doubles + threadIdx.x;
+  // blocks of W warps: each warp owns its own 32 columns; W > 1 adds a block barrier per loop iteration that keeps
+  // the SM's warps in the same phase (RHS / control), i.e. sharing instruction-cache fills
+  const int wib = threadIdx.x >> 5, lane_ = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  s.hot = prx_dyn_smem + (size_t)wib * 32 * Cell::hot_doubles() + lane_;
+  s.cold = cold + ((size_t)blockIdx.x * nwarp + wib) * 32 * cold_doubles + lane_;
   s.nz = p.qmax + 1;
   int cell = -1;
   bool exhausted = false;
@@ -671,7 +681,11 @@ __global__ void __launch_bounds__(32, PRX_BDF3_MINBLOCKS) PRX_CAT(bdf3_kernel_, 
         ls.masked++;
       }
     }
-    if (!__any_sync(FULL, !(exhausted && (cell < 0)))) {
+    if (nwarp > 1) {
+      if (!__syncthreads_or(!(exhausted && (cell < 0)))) {
+        break;
+      }
+    } else if (!__any_sync(FULL, !(exhausted && (cell < 0)))) {
       break;
     }
     // ---- (2) control ----
@@ -730,7 +744,7 @@ __global__ void __launch_bounds__(32, PRX_BDF3_MINBLOCKS) PRX_CAT(bdf3_kernel_, 
     }
     if (m_lu && ((__popc(m_lu) >= sp.lu_defer_min_lanes) || (m_rhs == 0))) {
       if (req == REQ_LU) {
-        s.lu_info = dense_getrf(s.A(), s.piv());
+        s.lu_info = (NEQ <= 12) ? dense_getrf_small(s.A(), s.piv()) : ((NEQ <= 24) ? dense_getrf_mid(s.A(), s.piv()) : dense_getrf(s.A(), s.piv()));
         req = REQ_NONE;
       }
       __syncwarp();
@@ -813,9 +827,10 @@ cudaError_t launch_bdf3(const BoxArgs& a, const BdfParams& p, const SchedParams&
 {
   typedef BdfStoreHot<32, TABRHS> Store;
   auto kern = PRX_CAT(bdf3_kernel_, PRX_MECH_SUFFIX)<TABRHS>;
-  const size_t smem = sizeof(double) * 32 * (size_t)Store::hot_doubles();
   const int cold_doubles = Store::cold_doubles(p.qmax);
   int dev = 0, sms = 148, per_sm = 0, max_optin = 0;
+  const int W0 = (sp.block_warps >= 1 && sp.block_warps <= 4) ? sp.block_warps : 1;
+  const size_t smem = sizeof(double) * 32 * W0 * (size_t)Store::hot_doubles();
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -827,23 +842,24 @@ cudaError_t launch_bdf3(const BoxArgs& a, const BdfParams& p, const SchedParams&
     return e;
   }
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem) != cudaSuccess || per_sm < 1) {
+  const int W = (sp.block_warps >= 1 && sp.block_warps <= 4) ? sp.block_warps : 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * W, smem) != cudaSuccess || per_sm < 1) {
     return cudaErrorInvalidConfiguration;
   }
-  if (sp.max_warps_per_sm > 0 && per_sm > sp.max_warps_per_sm) {
-    per_sm = sp.max_warps_per_sm;
+  if (sp.max_warps_per_sm > 0 && per_sm * W > sp.max_warps_per_sm) {
+    per_sm = sp.max_warps_per_sm / W > 0 ? sp.max_warps_per_sm / W : 1;
   }
   long long grid = (long long)sms * per_sm; // persistent: one full wave, a multiple of the SM count
-  const long long needed = ((long long)a.ncells + 31) / 32;
+  const long long needed = ((long long)a.ncells + 32 * W - 1) / (32 * W);
   grid = needed < grid ? needed : grid;
   double* cold = nullptr; // cold columns of the resident cells (stream-ordered, pool-backed after the first call)
-  e = cudaMallocAsync(&cold, sizeof(double) * (size_t)grid * 32 * cold_doubles, stream);
+  e = cudaMallocAsync(&cold, sizeof(double) * (size_t)grid * 32 * W * cold_doubles, stream);
   if (e != cudaSuccess) {
     return e;
   }
   e = cudaMemsetAsync(queue, 0, sizeof(int), stream);
   if (e == cudaSuccess) {
-    kern<<<(int)grid, 32, smem, stream>>>(a, p, sp, queue, stats, cold, cold_doubles);
+    kern<<<(int)grid, 32 * W, smem, stream>>>(a, p, sp, queue, stats, cold, cold_doubles);
     e = cudaGetLastError();
   }
   const cudaError_t e2 = cudaFreeAsync(cold, stream);
@@ -881,7 +897,7 @@ __device__ __noinline__ void jac_serial(const int reactor_type, const double* __
 template <int G>
 __global__ void __launch_bounds__(32, PRX_COOP_MINBLOCKS) PRX_CAT(bdfc_kernel_, PRX_MECH_SUFFIX)(
   const BoxArgs a, const BdfParams p, const SchedParams sp, int* __restrict__ queue, DevStats* __restrict__ stats,
-  double* __restrict__ jscratch, const int cell_doubles)
+  double* __restrict__ jscratch, double* __restrict__ ascratch, const int cell_doubles)
 {
   typedef BdfCellT<BdfStoreCoop<G>, SrcRef> Cell;
   constexpr int CPW = 32 / G; // cells per warp
@@ -891,6 +907,7 @@ __global__ void __launch_bounds__(32, PRX_COOP_MINBLOCKS) PRX_CAT(bdfc_kernel_, 
   const Grp<G>& g = s.g;
   s.base = prx_dyn_smem + (size_t)grp * cell_doubles;
   s.gJ = jscratch + ((size_t)blockIdx.x * CPW + grp) * (NEQ * NEQ);
+  s.gA = (ascratch != nullptr) ? ascratch + ((size_t)blockIdx.x * CPW + grp) * (NEQ * NEQ) : nullptr;
   s.nz = p.qmax + 1;
   int cell = -1;
   bool exhausted = false;
@@ -1098,7 +1115,9 @@ cudaError_t launch_bdfc(const BoxArgs& a, const BdfParams& p, const SchedParams&
 {
   auto kern = PRX_CAT(bdfc_kernel_, PRX_MECH_SUFFIX)<G>;
   constexpr int CPW = 32 / G;
-  const int cell_doubles = BdfStoreCoop<G>::doubles_per_cell(p.qmax);
+  // Newton matrix in the shared-memory block unless it is large (PRX_COOP_A_GLOBAL: 0 never, 1 always, else > 8 KB)
+  const bool a_global = (sp.coop_a_global == 1) || (sp.coop_a_global != 0 && sizeof(double) * NEQ * NEQ > 8192);
+  const int cell_doubles = BdfStoreCoop<G>::doubles_per_cell(p.qmax, a_global);
   const size_t smem = sizeof(double) * (size_t)CPW * cell_doubles;
   int dev = 0, sms = 148, per_sm = 0, max_optin = 0;
   cudaGetDevice(&dev);
@@ -1122,13 +1141,14 @@ cudaError_t launch_bdfc(const BoxArgs& a, const BdfParams& p, const SchedParams&
   const long long needed = ((long long)a.ncells + CPW - 1) / CPW;
   grid = needed < grid ? needed : grid;
   double* jscratch = nullptr; // savedJ slots, one per resident cell (stream-ordered, pool-backed after the first call)
-  e = cudaMallocAsync(&jscratch, sizeof(double) * (size_t)grid * CPW * NEQ * NEQ, stream);
+  e = cudaMallocAsync(&jscratch, sizeof(double) * (size_t)grid * CPW * NEQ * NEQ * (a_global ? 2 : 1), stream);
   if (e != cudaSuccess) {
     return e;
   }
+  double* ascratch = a_global ? jscratch + (size_t)grid * CPW * NEQ * NEQ : nullptr;
   e = cudaMemsetAsync(queue, 0, sizeof(int), stream);
   if (e == cudaSuccess) {
-    kern<<<(int)grid, 32, smem, stream>>>(a, p, sp, queue, stats, jscratch, cell_doubles);
+    kern<<<(int)grid, 32, smem, stream>>>(a, p, sp, queue, stats, jscratch, ascratch, cell_doubles);
     e = cudaGetLastError();
   }
   const cudaError_t e2 = cudaFreeAsync(jscratch, stream);

@@ -17,7 +17,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libpelerx_b200.so")
+LIB_PATH = os.environ.get("PRX_LIB_PATH") or os.path.join(HERE, "lib", "libpelerx_b200.so")  # override: A/B builds
 
 MECHANISMS = {"LiDryer": 0, "drm19": 1, "dodecane_lu": 2}
 REACTOR_KINDS = {"ReactorRK64": 0, "ReactorCvode": 1}

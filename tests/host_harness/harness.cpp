@@ -202,6 +202,28 @@ int hh_jac(int tab, int n, int reactor_type, const double* y, double* J)
   return 0;
 }
 
+// LU factor + solve of n column-major NEQ x NEQ systems: reference-order loops (small = 0) or the
+// register-staged device forms (small = 1); returns the sum of the GETRF return codes
+int hh_lu(int small, int n, double* A, int* piv, double* b)
+{
+  int rc = 0;
+  for (int s = 0; s < n; s++) {
+    double* a = A + (size_t)s * NEQ * NEQ;
+    int* p = piv + (size_t)s * NEQ;
+    double* x = b + (size_t)s * NEQ;
+    const int r = (small == 2) ? dense_getrf_mid(a, p) : (small ? dense_getrf_small(a, p) : dense_getrf(a, p));
+    rc += r;
+    if (r == 0) {
+      if (small) {
+        dense_getrs_small(a, p, x);
+      } else {
+        dense_getrs(a, p, x);
+      }
+    }
+  }
+  return rc;
+}
+
 int hh_react_rk64_variant(
   int tab, int reactor_type, double atol, int nsg, int nsmin, int nsmax, int ncells, double* rY,
   const double* rYsrc, double* T, double* rE, const double* rEsrc, double* FC, double dt, double time)

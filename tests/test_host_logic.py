@@ -201,3 +201,28 @@ def test_table_driven_jacobian_is_bit_identical(harness, mech, reactor_type):
         out.append(J)
     assert np.abs(out[0]).max() > 0 and np.all(np.isfinite(out[0]))
     assert np.array_equal(out[0], out[1])
+
+
+@pytest.mark.parametrize("mech", MECHS[:2])
+def test_register_staged_lu_is_bit_identical(harness, mech):
+    """dense_getrf_small / dense_getrs_small (loads of an elimination step hoisted above its stores) against the
+    reference-order loops: random systems, systems with tied pivots, zero entries and singular columns."""
+    hh = harness[mech]
+    NEQ = hh.hh_num_species() + 1
+    rng = np.random.default_rng(3)
+    n = 64
+    A = rng.standard_normal((n, NEQ, NEQ))
+    A[1::4] = np.round(A[1::4] * 2.0)            # ties and exact zeros
+    A[2::8, 3, :] = 0.0                           # a zero column (column-major: [col, row]) -> singular
+    A[5::8] += np.eye(NEQ) * 50.0
+    b = rng.standard_normal((n, NEQ))
+    res = []
+    for small in (0, 1, 2):
+        a, x = A.copy(), b.copy()
+        piv = np.zeros((n, NEQ), dtype=np.int32)
+        rc = hh.hh_lu(small, n, _p(a), piv.ctypes.data_as(ip), _p(x))
+        res.append((rc, a, piv, x))
+    for other in res[1:]:
+        assert res[0][0] == other[0] and res[0][0] > 0
+        for u, v in zip(res[0][1:], other[1:]):
+            assert np.array_equal(u, v, equal_nan=True)
