@@ -305,6 +305,8 @@ int prx_create(const prx_config* cfg, prx_handle** out)
   h->sched.bdf_variant = env_int("PRX_BDF_VARIANT", -1);
   h->sched.max_warps_per_sm = env_int("PRX_MAX_WARPS_PER_SM", 0);
   h->sched.coop_a_global = env_int("PRX_COOP_A_GLOBAL", -1);
+  h->sched.lu_defer_block = env_int("PRX_LU_DEFER_BLOCK", 0);
+  h->sched.lu_defer_max_age = env_int("PRX_LU_DEFER_AGE", 6);
   h->sched.block_warps = env_int("PRX_BLOCK_WARPS", 0); // 0: kernel default (gen-1: both block barriers; hot/cold: single warps)
   h->last_ncells = 0;
   h->d_stage = nullptr;

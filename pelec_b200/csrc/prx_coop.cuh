@@ -113,20 +113,37 @@ struct BdfStoreCoop
 
 // ---- dense LU / solve, G lanes per matrix ---------------------------------------------------------
 // Same pivot choice (first row of maximal magnitude) and the same per-entry operations as
-// SUNDlsMat_denseGETRF / denseGETRS; `a` is column-major NEQ x NEQ in shared memory.
+// SUNDlsMat_denseGETRF / denseGETRS; `a` is column-major NEQ x NEQ, in the cell's shared-memory block or - for
+// large systems - in a global (L2 resident) slot.  Lane gl owns rows gl, gl+G, ...  Memory accesses are issued in
+// batches of PRX_COOP_CB columns (all loads of a batch before its stores): with the matrix in global memory the
+// first version paid one dependent L2 round trip per entry of the trailing update and per column of a triangular
+// solve (ncu r01h: 54 % of all stall samples on those lines).
+#ifndef PRX_COOP_CB
+#define PRX_COOP_CB 4
+#endif
+
 template <int G>
 __device__ __forceinline__ int getrf_coop(const Grp<G>& g, double* __restrict__ a, int* __restrict__ piv)
 {
+  constexpr int RPL = (NEQ + G - 1) / G; // rows per lane
+  constexpr int CB = PRX_COOP_CB;
   g.sync();
 #pragma unroll 1
   for (int k = 0; k < NEQ; k++) {
     double* ck = a + k * NEQ;
+    double colv[RPL];
+#pragma unroll
+    for (int r = 0; r < RPL; r++) {
+      const int i = g.gl + r * G;
+      colv[r] = (i >= k && i < NEQ) ? ck[i] : 0.0;
+    }
     double best = -1.0;
     int bi = k;
-#pragma unroll 1
-    for (int i = k + g.gl; i < NEQ; i += G) {
-      const double v = fabs(ck[i]);
-      if (v > best) {
+#pragma unroll
+    for (int r = 0; r < RPL; r++) {
+      const int i = g.gl + r * G;
+      const double v = fabs(colv[r]);
+      if (i >= k && i < NEQ && v > best) {
         best = v;
         bi = i;
       }
@@ -140,7 +157,7 @@ __device__ __forceinline__ int getrf_coop(const Grp<G>& g, double* __restrict__ 
         bi = oi;
       }
     }
-    const int l = bi;
+    const int l = (best < 0.0) ? k : bi; // all-NaN column: the reference keeps l = k
     if (g.gl == 0) {
       piv[k] = l;
     }
@@ -158,29 +175,41 @@ __device__ __forceinline__ int getrf_coop(const Grp<G>& g, double* __restrict__ 
     }
     g.sync();
     const double mult = 1.0 / ck[k];
-#pragma unroll 1
-    for (int i = k + 1 + g.gl; i < NEQ; i += G) {
-      ck[i] *= mult;
-    }
-    g.sync();
-    // rank-1 update of the trailing (NEQ-k-1)^2 block, its entries dealt round-robin to the lanes
-    const int m = NEQ - k - 1;
-    int jj = 0, ii = g.gl;
-    while (ii >= m && jj < m) {
-      ii -= m;
-      jj++;
-    }
-#pragma unroll 1
-    while (jj < m) {
-      double* cj = a + (k + 1 + jj) * NEQ;
-      const double a_kj = cj[k];
-      if (a_kj != 0.0) {
-        cj[k + 1 + ii] -= a_kj * ck[k + 1 + ii];
+    double m[RPL]; // this lane's multipliers (column k below the diagonal), kept in registers for the update
+#pragma unroll
+    for (int r = 0; r < RPL; r++) {
+      const int i = g.gl + r * G;
+      m[r] = 0.0;
+      if (i > k && i < NEQ) {
+        m[r] = ck[i] * mult;
+        ck[i] = m[r];
       }
-      ii += G;
-      while (ii >= m && jj < m) {
-        ii -= m;
-        jj++;
+    }
+    // rank-1 update of the trailing block, CB columns per batch
+#pragma unroll 1
+    for (int j0 = k + 1; j0 < NEQ; j0 += CB) {
+      double akj[CB], x[CB][RPL];
+#pragma unroll
+      for (int c = 0; c < CB; c++) {
+        const int j = (j0 + c < NEQ) ? j0 + c : NEQ - 1;
+        akj[c] = a[j * NEQ + k];
+#pragma unroll
+        for (int r = 0; r < RPL; r++) {
+          const int i = g.gl + r * G;
+          x[c][r] = (i > k && i < NEQ) ? a[j * NEQ + i] : 0.0;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CB; c++) {
+        if (j0 + c < NEQ && akj[c] != 0.0) {
+#pragma unroll
+          for (int r = 0; r < RPL; r++) {
+            const int i = g.gl + r * G;
+            if (i > k && i < NEQ) {
+              a[(j0 + c) * NEQ + i] = x[c][r] - akj[c] * m[r];
+            }
+          }
+        }
       }
     }
     g.sync();
@@ -192,6 +221,8 @@ template <int G>
 __device__ __forceinline__ void getrs_coop(
   const Grp<G>& g, const double* __restrict__ a, const int* __restrict__ piv, double* __restrict__ b)
 {
+  constexpr int RPL = (NEQ + G - 1) / G;
+  constexpr int CB = PRX_COOP_CB;
   g.sync();
   if (g.gl == 0) { // row interchanges, in order
 #pragma unroll 1
@@ -205,31 +236,67 @@ __device__ __forceinline__ void getrs_coop(
     }
   }
   g.sync();
+  // L y = b: this lane's rows of CB columns are fetched together, then the CB eliminations run on shared memory
 #pragma unroll 1
-  for (int k = 0; k < NEQ - 1; k++) { // L y = b
-    const double bk = b[k];
-    const double* ck = a + k * NEQ;
-#pragma unroll 1
-    for (int i = k + 1 + g.gl; i < NEQ; i += G) {
-      b[i] -= ck[i] * bk;
+  for (int k0 = 0; k0 < NEQ - 1; k0 += CB) {
+    double lv[CB][RPL];
+#pragma unroll
+    for (int c = 0; c < CB; c++) {
+      const int k = k0 + c;
+#pragma unroll
+      for (int r = 0; r < RPL; r++) {
+        const int i = g.gl + r * G;
+        lv[c][r] = (k < NEQ - 1 && i > k && i < NEQ) ? a[k * NEQ + i] : 0.0;
+      }
     }
-    g.sync();
+#pragma unroll
+    for (int c = 0; c < CB; c++) {
+      const int k = k0 + c;
+      if (k < NEQ - 1) {
+        const double bk = b[k];
+#pragma unroll
+        for (int r = 0; r < RPL; r++) {
+          const int i = g.gl + r * G;
+          if (i > k && i < NEQ) {
+            b[i] -= lv[c][r] * bk;
+          }
+        }
+        g.sync();
+      }
+    }
   }
+  // U x = y, from the last column; every lane forms b[k]/a[k][k] itself, the owner of row k stores it
 #pragma unroll 1
-  for (int k = NEQ - 1; k > 0; k--) { // U x = y; every lane forms b[k]/a[k][k] itself, the owner stores it late
-    const double* ck = a + k * NEQ;
-    const double bk = b[k] / ck[k];
-#pragma unroll 1
-    for (int i = g.gl; i < k; i += G) {
-      b[i] -= ck[i] * bk;
+  for (int k0 = NEQ - 1; k0 >= 0; k0 -= CB) {
+    double uv[CB][RPL], dv[CB];
+#pragma unroll
+    for (int c = 0; c < CB; c++) {
+      const int k = k0 - c;
+      dv[c] = (k >= 0) ? a[k * NEQ + k] : 1.0;
+#pragma unroll
+      for (int r = 0; r < RPL; r++) {
+        const int i = g.gl + r * G;
+        uv[c][r] = (k >= 0 && i < k) ? a[k * NEQ + i] : 0.0;
+      }
     }
-    g.sync();
-    if (g.gl == 0) {
-      b[k] = bk;
+#pragma unroll
+    for (int c = 0; c < CB; c++) {
+      const int k = k0 - c;
+      if (k >= 0) {
+        const double bk = b[k] / dv[c];
+#pragma unroll
+        for (int r = 0; r < RPL; r++) {
+          const int i = g.gl + r * G;
+          if (i < k) {
+            b[i] -= uv[c][r] * bk;
+          }
+        }
+        g.sync();
+        if ((k & (G - 1)) == g.gl) {
+          b[k] = bk;
+        }
+      }
     }
-  }
-  if (g.gl == 0) {
-    b[0] /= a[0];
   }
   g.sync();
 }

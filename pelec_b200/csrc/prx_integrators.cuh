@@ -34,15 +34,32 @@
 // Loop pragmas of the BDF control code.  The device build keeps these loops ROLLED: the control code is
 // cheap arithmetic on shared-memory columns, and unrolling it (NEQ copies of every vector statement)
 // is what pushed the first kernel's hot loop far beyond the instruction cache.
+#ifndef PRX_VUNROLL_N
+#define PRX_VUNROLL_N 1
+#endif
 #ifndef PRX_VLOOP
 #ifdef PRX_HOST_TEST
 #define PRX_VLOOP
 #define PRX_MLOOP
 #define PRX_ILOOP
 #define PRX_UNROLL
+#define PRX_ALOOP
+#define PRX_QLOOP
 #else
+// one-thread-per-cell kernels with state in (L1/L2 backed) local memory: batches of independent loads
+#define PRX_ALOOP _Pragma("unroll 10") // A = I - gamma*J: savedJ -> A, entries independent
+#if PRX_VUNROLL_N > 1
+#define PRX_QLOOP _Pragma("unroll")    // Nordsieck-array loops over the order, constant trip count + predicate
+#else
+#define PRX_QLOOP _Pragma("unroll 1")
+#endif
 #define PRX_UNROLL _Pragma("unroll")
-#define PRX_VLOOP _Pragma("unroll 1") // per-component vector loops
+#ifndef PRX_VUNROLL_N
+#define PRX_VUNROLL_N 1
+#endif
+#define PRX_PRAGMA_(x) _Pragma(#x)
+#define PRX_PRAGMA(x) PRX_PRAGMA_(x)
+#define PRX_VLOOP PRX_PRAGMA(unroll PRX_VUNROLL_N) // per-component vector loops (-DPRX_VUNROLL_N=32: fully unrolled)
 #define PRX_MLOOP _Pragma("unroll 1") // column loops of the dense matrix code
 #define PRX_ILOOP _Pragma("unroll 2") // innermost row loops of the dense matrix code
 #endif
@@ -1241,7 +1258,7 @@ PRX_DEV int bdf_resume(Cell& s, const BdfParams& p)
             {
               const double mg = -s.gamma;
               s.sync();
-              PRX_MLOOP
+              PRX_ALOOP
               for (int e = s.vbegin(); e < NEQ * NEQ; e += s.vstep()) {
                 double v = s.savedJ()[e];
                 v *= mg;
@@ -1405,10 +1422,13 @@ PRX_DEV int bdf_resume(Cell& s, const BdfParams& p)
         s.tau[2] = s.tau[1];
       }
       s.tau[1] = s.h;
-      for (int j = 0; j <= s.q; j++) {
-        const double lj = s.l[j];
-        PRX_VEC_FOR(i) {
-          s.zn(j)[i] += lj * s.acor()[i];
+      PRX_QLOOP
+      for (int j = 0; j < LMAX; j++) { // j <= q, written with a constant trip count so that it can be unrolled
+        if (j <= s.q) {
+          const double lj = s.l[j];
+          PRX_VEC_FOR(i) {
+            s.zn(j)[i] += lj * s.acor()[i];
+          }
         }
       }
       s.qwait--;

@@ -307,6 +307,7 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
   int cell = -1;
   bool exhausted = false;
   int req = REQ_NONE;
+  int slow_age = 0;
   LaneStats ls = {};
   for (;;) {
     // ---- (1) refill ----
@@ -336,18 +337,33 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
       req = bdf_resume(s, p);
     }
     // ---- (3) serve ----
+    // Block-level batching of the slow requests (Jacobian, LU): with the phase barrier every iteration costs
+    // as much as its slowest warp, and with 8 warps almost every iteration had ONE warp factoring (ncu: 32 % of
+    // the stall samples on this barrier).  A warp with a slow request therefore waits (for at most
+    // lu_defer_max_age iterations) until lu_defer_block percent of the block's threads have one too, or until
+    // nobody in the block has RHS work; then they all factor in the same iteration.
+    bool slow_ok = true;
     if (sp.block_warps != 1 && sp.block_warps != 3) {
-      __syncthreads(); // re-align the warps after the divergent control code, right before the RHS
+      if (sp.lu_defer_block > 0) {
+        const int n_slow = __syncthreads_count(req == REQ_JAC || req == REQ_LU);
+        const int n_fast = __syncthreads_count(req == REQ_RHS);
+        slow_ok = (n_slow * 100 >= sp.lu_defer_block * (int)blockDim.x) || (n_fast == 0) || (slow_age >= sp.lu_defer_max_age);
+        if (req == REQ_JAC || req == REQ_LU) {
+          slow_age = slow_ok ? 0 : slow_age + 1;
+        }
+      } else {
+        __syncthreads(); // re-align the warps after the divergent control code, right before the RHS
+      }
     }
     const unsigned m_rhs = __ballot_sync(FULL, req == REQ_RHS);
-    const unsigned m_jac = __ballot_sync(FULL, req == REQ_JAC);
-    const unsigned m_lu = __ballot_sync(FULL, req == REQ_LU);
+    const unsigned m_jac = __ballot_sync(FULL, req == REQ_JAC && slow_ok);
+    const unsigned m_lu = __ballot_sync(FULL, req == REQ_LU && slow_ok);
     if (req == REQ_RHS) {
       rhs(s.t_eval, p.reactor_type, s.vec(s.in_sel), s.vec(s.out_sel), s.src);
       req = REQ_NONE;
     }
     if (m_jac && ((__popc(m_jac) >= sp.jac_defer_min_lanes) || (m_rhs == 0))) {
-      if (req == REQ_JAC) {
+      if (req == REQ_JAC && slow_ok) {
         double* J = s.savedJ(); // raw aJacobian output, scaled in place (each entry is read once, then written)
         jac_analytic(p.reactor_type, s.y(), J, [J](const int row, const int col, const double v) {
           J[col * NEQ + row] = v;
@@ -356,7 +372,7 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
       }
     }
     if (m_lu && ((__popc(m_lu) >= sp.lu_defer_min_lanes) || (m_rhs == 0))) {
-      if (req == REQ_LU) {
+      if (req == REQ_LU && slow_ok) {
         s.lu_info = (NEQ <= 12) ? dense_getrf_small(s.A(), s.piv()) : ((NEQ <= 24) ? dense_getrf_mid(s.A(), s.piv()) : dense_getrf(s.A(), s.piv()));
         req = REQ_NONE;
       }
@@ -1375,6 +1391,7 @@ cudaError_t launch_bdf(
   }
 #endif
   auto kern = PRX_CAT(bdf_kernel_, PRX_MECH_SUFFIX);
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1); // state lives in L1-cached local memory
   const int grid = persistent_grid((const void*)kern, a.ncells);
   cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(int), stream);
   if (e != cudaSuccess) {

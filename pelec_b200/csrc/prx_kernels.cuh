@@ -59,6 +59,8 @@ struct SchedParams
   int bdf_variant;      // BDF kernel generation (-1: the mechanism's default), see launch_bdf
   int max_warps_per_sm; // cap on resident warps of the shared-memory-column kernels (0: occupancy limit)
   int coop_a_global;    // cooperative kernel: Newton matrix in global memory (1), shared memory (0), by size (-1)
+  int lu_defer_block;   // gen-1 kernel: percent of the block's threads that must hold a Jacobian/LU request before they are served (0: off)
+  int lu_defer_max_age; // ... but never wait longer than this many iterations
   int block_warps;      // warps per block of the hot/cold kernel (1: independent warps; 2-4: phase-aligned by a block barrier)
 };
 

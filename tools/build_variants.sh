@@ -8,23 +8,18 @@ build() { # tag mech block minblocks variant
   local tag=$1 m=$2 b=$3 mb=$4 v=$5
   mkdir -p ../lib/obj_$tag
   nvcc $NVF -DPRX_MECH_HEADER="\"gen/mech_$m.cuh\"" -DPRX_MECH_SUFFIX=$m -DPRX_BLOCK=$b -DPRX_MINBLOCKS=$mb -DPRX_BDF_DEFAULT_VARIANT=$v \
-     -DPRX_COOP_MINBLOCKS=24 -c prx_kernels.cu -o ../lib/obj_$tag/kernels_$m.o 2> ../lib/obj_$tag/kernels_$m.log
+     -DPRX_COOP_MINBLOCKS=24 $EXTRA -c prx_kernels.cu -o ../lib/obj_$tag/kernels_$m.o 2> ../lib/obj_$tag/kernels_$m.log
 }
-for spec in "b256m2 256 2" "b128m4 128 4" "b128m6 128 6" "b64m8 64 8" "b256m1 256 1"; do
-  set -- $spec
-  build $1 LiDryer $2 $3 0 &
-done
-build d256m1 drm19 256 1 0 &
-build d128m2 drm19 128 2 0 &
-build d128m4 drm19 128 4 0 &
+EXTRA=""
+build vu1 LiDryer 256 2 0 &
+build dvu1 drm19 128 4 0 &
+EXTRA="-DPRX_VUNROLL_N=32"
+build vu32 LiDryer 256 2 0 &
+build dvu32 drm19 128 4 0 &
 wait
-for tag in b256m2 b128m4 b128m6 b64m8 b256m1; do
-  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../lib/libpelerx_b200_$tag.so ../lib/obj/api.o ../lib/obj_$tag/kernels_LiDryer.o \
-     ../lib/obj_d256m1/kernels_drm19.o ../lib/obj/kernels_dodecane_lu.o -Xlinker --version-script=exports.map -lcudart
-done
-for tag in d128m2 d128m4; do
-  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../lib/libpelerx_b200_$tag.so ../lib/obj/api.o ../lib/obj_b256m2/kernels_LiDryer.o \
-     ../lib/obj_$tag/kernels_drm19.o ../lib/obj/kernels_dodecane_lu.o -Xlinker --version-script=exports.map -lcudart
+for t in 1 32; do
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../lib/libpelerx_b200_vu$t.so ../lib/obj/api.o ../lib/obj_vu$t/kernels_LiDryer.o \
+     ../lib/obj_dvu$t/kernels_drm19.o ../lib/obj/kernels_dodecane_lu.o -Xlinker --version-script=exports.map -lcudart
 done
 ls -la ../lib/*.so
-grep -h -A2 "18bdf_kernel" ../lib/obj_*/kernels_*.log | grep "Used\|stack"
+for t in vu1 vu32 dvu1 dvu32; do grep -h -A2 "18bdf_kernel" ../lib/obj_$t/kernels_*.log | grep "Used\|stack"; done
