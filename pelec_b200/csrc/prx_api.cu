@@ -27,6 +27,8 @@ struct prx_handle
   double* d_stage;
   size_t d_stage_bytes;
   cudaStream_t stage_stream;
+  cudaStream_t in_stream, out_stream; // host staging pipeline of prx_react_box_host: H2D | react | D2H per slab
+  bool keep_last_steps;              // react_args: do not reset the per-call step sum (slabs of one call)
   char err[512];
 };
 
@@ -312,12 +314,17 @@ int prx_create(const prx_config* cfg, prx_handle** out)
   h->d_stage = nullptr;
   h->d_stage_bytes = 0;
   h->stage_stream = nullptr;
+  h->in_stream = nullptr;
+  h->out_stream = nullptr;
+  h->keep_last_steps = false;
   h->err[0] = 0;
   DeviceGuard g(dev);
   if (cudaMalloc(&h->d_stats, sizeof(DevStats)) != cudaSuccess ||
       cudaMalloc(&h->d_queues, sizeof(int) * h->n_queues) != cudaSuccess ||
       cudaMemset(h->d_stats, 0, sizeof(DevStats)) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->stage_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&h->stage_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking) != cudaSuccess) {
     cudaGetLastError();
     prx_destroy(h);
     return PRX_ERR_CUDA;
@@ -341,6 +348,12 @@ int prx_destroy(prx_handle* h)
   }
   if (h->d_stage) {
     cudaFree(h->d_stage);
+  }
+  if (h->in_stream) {
+    cudaStreamDestroy(h->in_stream);
+  }
+  if (h->out_stream) {
+    cudaStreamDestroy(h->out_stream);
   }
   if (h->stage_stream) {
     cudaStreamDestroy(h->stage_stream);
@@ -369,8 +382,11 @@ static int react_args(prx_handle* h, const BoxArgs& a, cudaStream_t stream)
 {
   DeviceGuard g(h->device);
   // per-launch step sum (for the value ReactorBase::react returns)
-  PRX_CUDA(h, cudaMemsetAsync(&h->d_stats->v[ST_LAST_STEPS], 0, sizeof(unsigned long long), stream));
-  h->last_ncells = a.ncells;
+  if (!h->keep_last_steps) {
+    PRX_CUDA(h, cudaMemsetAsync(&h->d_stats->v[ST_LAST_STEPS], 0, sizeof(unsigned long long), stream));
+    h->last_ncells = 0;
+  }
+  h->last_ncells += a.ncells;
   cudaError_t e;
   if (h->cfg.reactor_kind == PRX_REACTOR_RK64) {
     e = h->ops->launch_rk64(a, h->cfg, next_queue(h), h->d_stats, stream);
@@ -486,21 +502,16 @@ int prx_react_box_host(
   double* d_rEsrc = d_rE + nc;
   double* d_FC = d_rEsrc + nc;
   int* d_mask = reinterpret_cast<int*>(d_FC + nc);
-  PRX_CUDA(h, cudaMemcpyAsync(d_rY, rY, sizeof(double) * N * nc, cudaMemcpyHostToDevice, st));
-  PRX_CUDA(h, cudaMemcpyAsync(d_rYsrc, rYsrc, sizeof(double) * N * nc, cudaMemcpyHostToDevice, st));
-  PRX_CUDA(h, cudaMemcpyAsync(d_T, T, sizeof(double) * nc, cudaMemcpyHostToDevice, st));
-  PRX_CUDA(h, cudaMemcpyAsync(d_rE, rE, sizeof(double) * nc, cudaMemcpyHostToDevice, st));
-  PRX_CUDA(h, cudaMemcpyAsync(d_rEsrc, rEsrc, sizeof(double) * nc, cudaMemcpyHostToDevice, st));
-  if (mask != nullptr) {
-    PRX_CUDA(h, cudaMemcpyAsync(d_mask, mask, sizeof(int) * nc, cudaMemcpyHostToDevice, st));
-  }
-  const int lo[3] = {0, 0, 0};
-  const int hi[3] = {nx - 1, ny - 1, nz - 1};
+  // Slab pipeline: the box is cut along k into up to 4 slabs; slab s+1 is copied in while slab s reacts and slab
+  // s-1 is copied out (three streams, full-duplex PCIe).  Every array is SoA with component stride nc, so one slab
+  // of one array is a 2-D copy: rows = components (pitch nc), row length = the slab's cells.
+  const long long plane = (long long)nx * ny;
+  int nslab = (nz >= 8 && nc >= (1LL << 18)) ? 4 : 1;
   auto mk = [&](double* p, int ncomp) {
     prx_array4 a;
     a.p = p;
     a.jstride = nx;
-    a.kstride = (long long)nx * ny;
+    a.kstride = plane;
     a.nstride = nc;
     a.begin[0] = a.begin[1] = a.begin[2] = 0;
     a.end[0] = nx;
@@ -514,22 +525,67 @@ int prx_react_box_host(
   prx_array4i a_mask;
   a_mask.p = (mask != nullptr) ? d_mask : nullptr;
   a_mask.jstride = nx;
-  a_mask.kstride = (long long)nx * ny;
+  a_mask.kstride = plane;
   a_mask.nstride = nc;
   a_mask.begin[0] = a_mask.begin[1] = a_mask.begin[2] = 0;
   a_mask.end[0] = nx;
   a_mask.end[1] = ny;
   a_mask.end[2] = nz;
   a_mask.ncomp = 1;
-  const int r = prx_react_box(h, lo, hi, &a_rY, &a_rYsrc, &a_T, &a_rE, &a_rEsrc, &a_FC, &a_mask, dt, time, st);
-  if (r != PRX_OK) {
-    return r;
+  cudaEvent_t ev_in[4], ev_done[4];
+  for (int sidx = 0; sidx < nslab; sidx++) {
+    PRX_CUDA(h, cudaEventCreateWithFlags(&ev_in[sidx], cudaEventDisableTiming));
+    PRX_CUDA(h, cudaEventCreateWithFlags(&ev_done[sidx], cudaEventDisableTiming));
   }
-  PRX_CUDA(h, cudaMemcpyAsync(rY, d_rY, sizeof(double) * N * nc, cudaMemcpyDeviceToHost, st));
-  PRX_CUDA(h, cudaMemcpyAsync(T, d_T, sizeof(double) * nc, cudaMemcpyDeviceToHost, st));
-  PRX_CUDA(h, cudaMemcpyAsync(rE, d_rE, sizeof(double) * nc, cudaMemcpyDeviceToHost, st));
-  PRX_CUDA(h, cudaMemcpyAsync(FC, d_FC, sizeof(double) * nc, cudaMemcpyDeviceToHost, st));
-  PRX_CUDA(h, cudaStreamSynchronize(st));
+  auto copy2d = [&](void* dst, const void* src, size_t elem, long long off, long long cells, int ncomp, cudaMemcpyKind kind,
+                    cudaStream_t strm) {
+    return cudaMemcpy2DAsync(
+      (char*)dst + off * elem, (size_t)nc * elem, (const char*)src + off * elem, (size_t)nc * elem, (size_t)cells * elem,
+      (size_t)ncomp, kind, strm);
+  };
+  int rc_react = PRX_OK;
+  h->keep_last_steps = false;
+  for (int sidx = 0; sidx < nslab && rc_react == PRX_OK; sidx++) {
+    const int k0 = (int)((long long)nz * sidx / nslab), k1 = (int)((long long)nz * (sidx + 1) / nslab);
+    const long long off = plane * k0, cells = plane * (k1 - k0);
+    PRX_CUDA(h, copy2d(d_rY, rY, sizeof(double), off, cells, N, cudaMemcpyHostToDevice, h->in_stream));
+    PRX_CUDA(h, copy2d(d_rYsrc, rYsrc, sizeof(double), off, cells, N, cudaMemcpyHostToDevice, h->in_stream));
+    PRX_CUDA(h, copy2d(d_T, T, sizeof(double), off, cells, 1, cudaMemcpyHostToDevice, h->in_stream));
+    PRX_CUDA(h, copy2d(d_rE, rE, sizeof(double), off, cells, 1, cudaMemcpyHostToDevice, h->in_stream));
+    PRX_CUDA(h, copy2d(d_rEsrc, rEsrc, sizeof(double), off, cells, 1, cudaMemcpyHostToDevice, h->in_stream));
+    if (mask != nullptr) {
+      PRX_CUDA(h, copy2d(d_mask, mask, sizeof(int), off, cells, 1, cudaMemcpyHostToDevice, h->in_stream));
+    }
+    PRX_CUDA(h, cudaEventRecord(ev_in[sidx], h->in_stream));
+    PRX_CUDA(h, cudaStreamWaitEvent(st, ev_in[sidx], 0));
+    const int lo[3] = {0, 0, k0};
+    const int hi[3] = {nx - 1, ny - 1, k1 - 1};
+    rc_react = prx_react_box(h, lo, hi, &a_rY, &a_rYsrc, &a_T, &a_rE, &a_rEsrc, &a_FC, &a_mask, dt, time, st);
+    h->keep_last_steps = true; // the following slabs belong to the same react call
+    if (rc_react != PRX_OK) {
+      break;
+    }
+    PRX_CUDA(h, cudaEventRecord(ev_done[sidx], st));
+    PRX_CUDA(h, cudaStreamWaitEvent(h->out_stream, ev_done[sidx], 0));
+    PRX_CUDA(h, copy2d(rY, d_rY, sizeof(double), off, cells, N, cudaMemcpyDeviceToHost, h->out_stream));
+    PRX_CUDA(h, copy2d(T, d_T, sizeof(double), off, cells, 1, cudaMemcpyDeviceToHost, h->out_stream));
+    PRX_CUDA(h, copy2d(rE, d_rE, sizeof(double), off, cells, 1, cudaMemcpyDeviceToHost, h->out_stream));
+    PRX_CUDA(h, copy2d(FC, d_FC, sizeof(double), off, cells, 1, cudaMemcpyDeviceToHost, h->out_stream));
+  }
+  h->keep_last_steps = false;
+  cudaError_t es = cudaStreamSynchronize(h->out_stream);
+  cudaError_t es2 = cudaStreamSynchronize(st);
+  cudaError_t es3 = cudaStreamSynchronize(h->in_stream);
+  for (int sidx = 0; sidx < nslab; sidx++) {
+    cudaEventDestroy(ev_in[sidx]);
+    cudaEventDestroy(ev_done[sidx]);
+  }
+  if (rc_react != PRX_OK) {
+    return rc_react;
+  }
+  PRX_CUDA(h, es);
+  PRX_CUDA(h, es2);
+  PRX_CUDA(h, es3);
   return PRX_OK;
 }
 

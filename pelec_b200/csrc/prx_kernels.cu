@@ -31,6 +31,9 @@
 #define PRX_MINBLOCKS 1
 #endif
 
+#ifndef PRX_INLINE_SLOW
+#define PRX_INLINE_SLOW 0
+#endif
 #ifndef PRX_BDF_DEFAULT_VARIANT
 #define PRX_BDF_DEFAULT_VARIANT 0
 #endif
@@ -299,6 +302,10 @@ __device__ __forceinline__ double* bdf_vec(BdfCell& s, const int sel)
   }
 }
 
+// one cell per thread with the straight-line generated Jacobian only makes sense for small mechanisms (and the
+// 16k-line dodecane_lu Jacobian costs six minutes of compile time): large ones use the cooperative kernel
+#define PRX_HAVE_BDF1 (PRX_NUM_SPECIES <= 32)
+#if PRX_HAVE_BDF1
 __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_, PRX_MECH_SUFFIX)(
   const BoxArgs a, const BdfParams p, const SchedParams sp, int* __restrict__ queue,
   DevStats* __restrict__ stats)
@@ -324,8 +331,10 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
         ls.masked++;
       }
     }
-    // exit test; with sp.block_warps != 1 it is block wide and doubles as the phase barrier (see rk64 kernel)
-    if (sp.block_warps != 1) {
+    // exit test; with sp.block_warps != 1 it is block wide and doubles as the phase barrier (see rk64 kernel);
+    // mode 2 has a single barrier per iteration, the one in front of the RHS, which then carries the exit test
+    if (sp.block_warps == 2) {
+    } else if (sp.block_warps != 1) {
       if (!__syncthreads_or(!(exhausted && (cell < 0)))) {
         break;
       }
@@ -333,9 +342,33 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
       break;
     }
     // ---- (2) control ----
+#if PRX_INLINE_SLOW
+    // Jacobian / LU requests are served inside the control phase (warp-level loop), so that every iteration of
+    // the block ends in exactly one RHS evaluation per warp and no iteration is spent on one warp's factorisation
+    for (;;) {
+      if (cell >= 0 && req == REQ_NONE) {
+        req = bdf_resume(s, p);
+      }
+      if (__ballot_sync(FULL, req == REQ_JAC || req == REQ_LU) == 0u) {
+        break;
+      }
+      if (req == REQ_JAC) {
+        double* J = s.savedJ();
+        jac_analytic(p.reactor_type, s.y(), J, [J](const int row, const int col, const double v) {
+          J[col * NEQ + row] = v;
+        });
+        req = REQ_NONE;
+      }
+      if (req == REQ_LU) {
+        s.lu_info = (NEQ <= 12) ? dense_getrf_small(s.A(), s.piv()) : ((NEQ <= 24) ? dense_getrf_mid(s.A(), s.piv()) : dense_getrf(s.A(), s.piv()));
+        req = REQ_NONE;
+      }
+    }
+#else
     if (cell >= 0 && req == REQ_NONE) {
       req = bdf_resume(s, p);
     }
+#endif
     // ---- (3) serve ----
     // Block-level batching of the slow requests (Jacobian, LU): with the phase barrier every iteration costs
     // as much as its slowest warp, and with 8 warps almost every iteration had ONE warp factoring (ncu: 32 % of
@@ -343,7 +376,11 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
     // lu_defer_max_age iterations) until lu_defer_block percent of the block's threads have one too, or until
     // nobody in the block has RHS work; then they all factor in the same iteration.
     bool slow_ok = true;
-    if (sp.block_warps != 1 && sp.block_warps != 3) {
+    if (sp.block_warps == 2) {
+      if (!__syncthreads_or(!(exhausted && (cell < 0)))) {
+        break;
+      }
+    } else if (sp.block_warps != 1 && sp.block_warps != 3) {
       if (sp.lu_defer_block > 0) {
         const int n_slow = __syncthreads_count(req == REQ_JAC || req == REQ_LU);
         const int n_fast = __syncthreads_count(req == REQ_RHS);
@@ -362,6 +399,7 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
       rhs(s.t_eval, p.reactor_type, s.vec(s.in_sel), s.vec(s.out_sel), s.src);
       req = REQ_NONE;
     }
+#if !PRX_INLINE_SLOW
     if (m_jac && ((__popc(m_jac) >= sp.jac_defer_min_lanes) || (m_rhs == 0))) {
       if (req == REQ_JAC && slow_ok) {
         double* J = s.savedJ(); // raw aJacobian output, scaled in place (each entry is read once, then written)
@@ -377,6 +415,7 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
         req = REQ_NONE;
       }
     }
+#endif
     if (req == REQ_DONE) {
       store_cell(
         a, cell, s.y(), s.src, p.reactor_type, double(s.nfe + s.nfeDQ), p.clean_init_massfrac,
@@ -397,6 +436,7 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
   }
   flush_stats(ls, stats);
 }
+#endif // PRX_HAVE_BDF1
 
 // =====================================================================================
 // BDF kernel, second generation: integrator state in SHARED-MEMORY COLUMNS + table-driven RHS
@@ -1214,7 +1254,11 @@ __global__ void PRX_CAT(probe_jac_kernel_, PRX_MECH_SUFFIX)(
   }
   double* Jt = scratch + (long long)s * NEQ * NEQ;
   double* Jo = J + (long long)s * NEQ * NEQ;
+#if PRX_HAVE_BDF1
   jac_analytic(reactor_type, yy, Jt, [Jo](const int row, const int col, const double v) { Jo[col * NEQ + row] = v; });
+#else
+  jac_analytic_tab<TabG>(reactor_type, yy, Jt, [Jo](const int row, const int col, const double v) { Jo[col * NEQ + row] = v; });
+#endif
 }
 
 // =====================================================================================
@@ -1390,6 +1434,7 @@ cudaError_t launch_bdf(
     return launch_bdf3<true>(a, p, sp, queue, stats, stream);
   }
 #endif
+#if PRX_HAVE_BDF1
   auto kern = PRX_CAT(bdf_kernel_, PRX_MECH_SUFFIX);
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1); // state lives in L1-cached local memory
   const int grid = persistent_grid((const void*)kern, a.ncells);
@@ -1399,6 +1444,9 @@ cudaError_t launch_bdf(
   }
   kern<<<grid, PRX_BLOCK, 0, stream>>>(a, p, sp, queue, stats);
   return cudaGetLastError();
+#else
+  return launch_bdfc<32>(a, p, sp, queue, stats, stream);
+#endif
 }
 
 #define PRX_STR2(x) #x
@@ -1414,6 +1462,11 @@ int effective_bdf_variant(const SchedParams& sp)
 #if !PRX_HAVE_BDF2
   if (v >= 1 && v <= 4) {
     v = 0;
+  }
+#endif
+#if !PRX_HAVE_BDF1
+  if (v == 0) {
+    v = 32;
   }
 #endif
   return v;
