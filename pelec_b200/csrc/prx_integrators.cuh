@@ -281,7 +281,8 @@ struct BdfStoreLocal : public SerialOwner
   typedef double* Mat;
   double zn_[LMAX][NEQ], ewt_[NEQ], acor_[NEQ], tempv_[NEQ], ftemp_[NEQ], y_[NEQ], delta_[NEQ];
   double A_[NEQ * NEQ], savedJ_[NEQ * NEQ];
-  int piv_[NEQ];
+  int piv_[NEQ], perm_[NEQ];
+  PRX_MEM int* perm() { return perm_; }
   PRX_MEM Vec zn(const int j) { return zn_[j]; }
   PRX_MEM Vec ewt() { return ewt_; }
   PRX_MEM Vec acor() { return acor_; }
@@ -304,7 +305,8 @@ struct BdfStoreSmem : public SerialOwner
   double* base; // this thread's column of the block's dynamic shared memory
   int nz;       // number of zn slots (qmax + 1)
   double A_[A_SMEM ? 1 : NEQ * NEQ], savedJ_[NEQ * NEQ];
-  int piv_[NEQ];
+  int piv_[NEQ], perm_[NEQ];
+  PRX_MEM int* perm() { return perm_; }
   // vector slots after zn: ewt, acor, tempv, ftemp, y, delta, then N scratch doubles (chemistry), then A
   static PRX_HD int doubles_per_thread(const int qmax) { return (qmax + 1 + 6) * NEQ + N + (A_SMEM ? NEQ * NEQ : 0); }
   PRX_MEM Vec slot(const int s) const { return Vec{base + s * NEQ * STRIDE}; }
@@ -339,7 +341,8 @@ struct BdfStoreHot : public SerialOwner
   double* cold;
   int nz;
   double savedJ_[NEQ * NEQ];
-  int piv_[NEQ];
+  int piv_[NEQ], perm_[NEQ];
+  PRX_MEM int* perm() { return perm_; }
   static PRX_HD int hot_doubles() { return 7 * NEQ + (SCRATCH ? N : 0); }
   static PRX_HD int cold_doubles(const int qmax) { return (qmax > 1 ? qmax - 1 : 0) * NEQ + NEQ + NEQ * NEQ; }
   PRX_MEM Vec hslot(const int s) const { return Vec{hot + s * NEQ * STRIDE}; }
@@ -703,8 +706,14 @@ PRX_DEV void dense_getrs(MA a, const int* p, VB b)
 // per-entry arithmetic in the same order, but with compile-time row/column offsets and all loads of a step
 // issued before its stores, so the accesses of one elimination step are in flight together.
 template <class MA>
-PRX_DEV int dense_getrf_small(MA a, int* p)
+PRX_DEV int dense_getrf_small(MA a, int* p, int* perm = nullptr)
 {
+  if (perm != nullptr) { // composed row permutation, so that a solve gathers b in one step (see dense_getrs_small)
+    PRX_UNROLL
+    for (int i = 0; i < NEQ; i++) {
+      perm[i] = i;
+    }
+  }
   PRX_MLOOP
   for (int k = 0; k < NEQ; k++) {
     const int ck = k * NEQ;
@@ -731,6 +740,11 @@ PRX_UNROLL
       }
     }
     p[k] = l;
+    if (perm != nullptr && l != k) {
+      const int t = perm[k];
+      perm[k] = perm[l];
+      perm[l] = t;
+    }
     if (pv == 0.0) {
       return k + 1;
     }
@@ -787,8 +801,14 @@ PRX_UNROLL
 // Same, for mid-size systems (NEQ <= 24): the column loop stays rolled (one memory round trip per column
 // instead of one per entry), rows are compile-time offsets; row interchanges in chunks of 8 columns.
 template <class MA>
-PRX_DEV int dense_getrf_mid(MA a, int* p)
+PRX_DEV int dense_getrf_mid(MA a, int* p, int* perm = nullptr)
 {
+  if (perm != nullptr) {
+    PRX_UNROLL
+    for (int i = 0; i < NEQ; i++) {
+      perm[i] = i;
+    }
+  }
   PRX_MLOOP
   for (int k = 0; k < NEQ; k++) {
     const int ck = k * NEQ;
@@ -815,6 +835,11 @@ PRX_DEV int dense_getrf_mid(MA a, int* p)
       }
     }
     p[k] = l;
+    if (perm != nullptr && l != k) {
+      const int t = perm[k];
+      perm[k] = perm[l];
+      perm[l] = t;
+    }
     if (pv == 0.0) {
       return k + 1;
     }
@@ -869,21 +894,28 @@ PRX_DEV int dense_getrf_mid(MA a, int* p)
 }
 
 template <class MA, class VB>
-PRX_DEV void dense_getrs_small(MA a, const int* p, VB b)
+PRX_DEV void dense_getrs_small(MA a, const int* p, VB b, const int* perm = nullptr)
 {
-  PRX_MLOOP
-  for (int k = 0; k < NEQ; k++) {
-    const int pk = p[k];
-    if (pk != k) {
-      const double tmp = b[k];
-      b[k] = b[pk];
-      b[pk] = tmp;
-    }
-  }
   double bb[NEQ];
-PRX_UNROLL
-  for (int i = 0; i < NEQ; i++) {
-    bb[i] = b[i];
+  if (perm != nullptr) { // the NEQ row interchanges at once: independent gathers instead of a dependent swap chain
+    PRX_UNROLL
+    for (int i = 0; i < NEQ; i++) {
+      bb[i] = b[perm[i]];
+    }
+  } else {
+    PRX_MLOOP
+    for (int k = 0; k < NEQ; k++) {
+      const int pk = p[k];
+      if (pk != k) {
+        const double tmp = b[k];
+        b[k] = b[pk];
+        b[pk] = tmp;
+      }
+    }
+    PRX_UNROLL
+    for (int i = 0; i < NEQ; i++) {
+      bb[i] = b[i];
+    }
   }
 PRX_UNROLL
   for (int k = 0; k < NEQ - 1; k++) {
@@ -912,7 +944,7 @@ PRX_MEM void BdfStoreLocal::getrs(MA a, const int* p, VB b)
 {
 #ifndef PRX_HOST_TEST
   if (NEQ <= 24) {
-    dense_getrs_small(a, p, b);
+    dense_getrs_small(a, p, b, perm_);
     return;
   }
 #endif
@@ -924,7 +956,7 @@ PRX_MEM void BdfStoreSmem<STRIDE, A_SMEM>::getrs(MA a, const int* p, VB b)
 {
 #ifndef PRX_HOST_TEST
   if (NEQ <= 24) {
-    dense_getrs_small(a, p, b);
+    dense_getrs_small(a, p, b, perm_);
     return;
   }
 #endif
@@ -937,7 +969,7 @@ PRX_MEM void BdfStoreHot<STRIDE, SCRATCH>::getrs(MA a, const int* p, VB b)
 {
 #ifndef PRX_HOST_TEST
   if (NEQ <= 24) {
-    dense_getrs_small(a, p, b);
+    dense_getrs_small(a, p, b, perm_);
     return;
   }
 #endif
@@ -1258,14 +1290,28 @@ PRX_DEV int bdf_resume(Cell& s, const BdfParams& p)
             {
               const double mg = -s.gamma;
               s.sync();
-              PRX_ALOOP
-              for (int e = s.vbegin(); e < NEQ * NEQ; e += s.vstep()) {
-                double v = s.savedJ()[e];
-                v *= mg;
-                if (e % (NEQ + 1) == 0) { // diagonal of the column-major matrix
-                  v += 1.0;
+              if (s.vstep() == 1) { // one thread per cell: column by column, the diagonal test is compile-time
+                PRX_ALOOP
+                for (int j = 0; j < NEQ; j++) {
+                  PRX_VEC_FOR(i) {
+                    double v = s.savedJ()[j * NEQ + i];
+                    v *= mg;
+                    if (i == j) {
+                      v += 1.0;
+                    }
+                    s.A()[j * NEQ + i] = v;
+                  }
                 }
-                s.A()[e] = v;
+              } else {
+                PRX_ALOOP
+                for (int e = s.vbegin(); e < NEQ * NEQ; e += s.vstep()) {
+                  double v = s.savedJ()[e];
+                  v *= mg;
+                  if (e % (NEQ + 1) == 0) { // diagonal of the column-major matrix
+                    v += 1.0;
+                  }
+                  s.A()[e] = v;
+                }
               }
             }
             PRX_YIELD(6, REQ_LU); // kernel factors A in place, sets piv and lu_info

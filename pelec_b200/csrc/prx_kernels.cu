@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
         req = REQ_NONE;
       }
       if (req == REQ_LU) {
-        s.lu_info = (NEQ <= 12) ? dense_getrf_small(s.A(), s.piv()) : ((NEQ <= 24) ? dense_getrf_mid(s.A(), s.piv()) : dense_getrf(s.A(), s.piv()));
+        s.lu_info = (NEQ <= 12) ? dense_getrf_small(s.A(), s.piv(), s.perm()) : ((NEQ <= 24) ? dense_getrf_mid(s.A(), s.piv(), s.perm()) : dense_getrf(s.A(), s.piv()));
         req = REQ_NONE;
       }
     }
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
     }
     if (m_lu && ((__popc(m_lu) >= sp.lu_defer_min_lanes) || (m_rhs == 0))) {
       if (req == REQ_LU && slow_ok) {
-        s.lu_info = (NEQ <= 12) ? dense_getrf_small(s.A(), s.piv()) : ((NEQ <= 24) ? dense_getrf_mid(s.A(), s.piv()) : dense_getrf(s.A(), s.piv()));
+        s.lu_info = (NEQ <= 12) ? dense_getrf_small(s.A(), s.piv(), s.perm()) : ((NEQ <= 24) ? dense_getrf_mid(s.A(), s.piv(), s.perm()) : dense_getrf(s.A(), s.piv()));
         req = REQ_NONE;
       }
     }
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(32) PRX_CAT(bdf2_kernel_, PRX_MECH_SUFFIX)(
     }
     if (m_lu && ((__popc(m_lu) >= sp.lu_defer_min_lanes) || (m_rhs == 0))) {
       if (req == REQ_LU) {
-        s.lu_info = (NEQ <= 12) ? dense_getrf_small(s.A(), s.piv()) : ((NEQ <= 24) ? dense_getrf_mid(s.A(), s.piv()) : dense_getrf(s.A(), s.piv()));
+        s.lu_info = (NEQ <= 12) ? dense_getrf_small(s.A(), s.piv(), s.perm()) : ((NEQ <= 24) ? dense_getrf_mid(s.A(), s.piv(), s.perm()) : dense_getrf(s.A(), s.piv()));
         req = REQ_NONE;
       }
       __syncwarp();
@@ -800,7 +800,7 @@ __global__ void __launch_bounds__(128, PRX_BDF3_MINBLOCKS / 4) PRX_CAT(bdf3_kern
     }
     if (m_lu && ((__popc(m_lu) >= sp.lu_defer_min_lanes) || (m_rhs == 0))) {
       if (req == REQ_LU) {
-        s.lu_info = (NEQ <= 12) ? dense_getrf_small(s.A(), s.piv()) : ((NEQ <= 24) ? dense_getrf_mid(s.A(), s.piv()) : dense_getrf(s.A(), s.piv()));
+        s.lu_info = (NEQ <= 12) ? dense_getrf_small(s.A(), s.piv(), s.perm()) : ((NEQ <= 24) ? dense_getrf_mid(s.A(), s.piv(), s.perm()) : dense_getrf(s.A(), s.piv()));
         req = REQ_NONE;
       }
       __syncwarp();

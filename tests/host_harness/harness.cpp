@@ -211,11 +211,13 @@ int hh_lu(int small, int n, double* A, int* piv, double* b)
     double* a = A + (size_t)s * NEQ * NEQ;
     int* p = piv + (size_t)s * NEQ;
     double* x = b + (size_t)s * NEQ;
-    const int r = (small == 2) ? dense_getrf_mid(a, p) : (small ? dense_getrf_small(a, p) : dense_getrf(a, p));
+    int perm[NEQ];
+    int* pm = (s % 2) ? perm : nullptr; // both row-interchange forms of the staged solve
+    const int r = (small == 2) ? dense_getrf_mid(a, p, pm) : (small ? dense_getrf_small(a, p, pm) : dense_getrf(a, p));
     rc += r;
     if (r == 0) {
       if (small) {
-        dense_getrs_small(a, p, x);
+        dense_getrs_small(a, p, x, pm);
       } else {
         dense_getrs(a, p, x);
       }
