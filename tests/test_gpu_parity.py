@@ -327,3 +327,30 @@ def test_every_bdf_kernel_generation_matches_golden(mech, variant, monkeypatch):
     st = r.stats()
     assert st["cells"] == int(live.sum()) and st["cells_masked"] == int((~live).sum()) and st["n_failed"] == 0
     r.close()
+
+
+def test_enthalpy_form_matches_oracle(mech):
+    """reactor_type = 2 (rho*h advanced, constant pressure: GET_T_GIVEN_HY, cp, h_k, consP Jacobian) through the default
+    kernels, against the oracle (pinned to the reference for this form in tests/test_oracle.py)."""
+    orc = Oracle(mech)
+    g = golden(mech)
+    dt = float(g["dt"])
+    kw = CVODE_SETTINGS[1]
+    base = golden_state(g)
+    base.rE = base.rE + 1013250.0  # the golden states are at 1 atm: rho*h = rho*e + p
+    a, b = base.copy(), base.copy()
+    r = ReactorB200.create("ReactorCvode", mech, **cvode_parm(kw))
+    r.init(2, 1)
+    react_host(r, a, dt)
+    orc.react_cvode(b, dt, reactor_type=2, **kw)
+    assert_cvode_parity(a.rY, a.T, b.rY, b.T, kw["atol"], kw["rtol"])
+    assert np.array_equal(a.rE, b.rE) and r.stats()["n_failed"] == 0
+    r.close()
+    if "rk64_rY" in g:
+        a, b = base.copy(), base.copy()
+        r = ReactorB200.create("ReactorRK64", mech, ode__atol=1e-10)
+        r.init(2, 1)
+        react_host(r, a, dt)
+        orc.react_rk64(b, dt, atol=1e-10, reactor_type=2)
+        assert_rk64_parity(a.rY, a.T, b.rY, b.T)
+        r.close()

@@ -19,6 +19,8 @@ timeout 600 python bench.py --mech drm19 --n 64 --no-cpu-baseline 2>>gpurun_out/
 timeout 900 python bench.py --mech drm19 --n 128 --steps 3 --no-cpu-baseline 2>>gpurun_out/${TAG}_bench.err > gpurun_out/${TAG}_bench_drm19_cvode_128.json
 timeout 900 python bench.py --mech dodecane_lu --n 32 --steps 3 --no-cpu-baseline 2>>gpurun_out/${TAG}_bench.err > gpurun_out/${TAG}_bench_dodecane_cvode_32.json
 timeout 600 python bench.py --rtol 1e-6 --atol 1e-10 --max-order 2 --no-cpu-baseline 2>>gpurun_out/${TAG}_bench.err > gpurun_out/${TAG}_bench_lidryer_cvode_128_pelec_tols.json
+PRX_BLOCK_WARPS=1 timeout 600 python bench.py --steps 3 --no-cpu-baseline 2>>gpurun_out/${TAG}_bench.err > gpurun_out/${TAG}_bench_x_lidryer_no_barrier.json
+PRX_BLOCK_WARPS=1 timeout 600 python bench.py --steps 3 --mech drm19 --n 64 --no-cpu-baseline 2>>gpurun_out/${TAG}_bench.err > gpurun_out/${TAG}_bench_x_drm19_no_barrier.json
 python - <<PY
 import json, glob
 for f in sorted(glob.glob("gpurun_out/${TAG}_bench_*.json")):
