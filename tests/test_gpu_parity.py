@@ -352,5 +352,9 @@ def test_enthalpy_form_matches_oracle(mech):
         r.init(2, 1)
         react_host(r, a, dt)
         orc.react_rk64(b, dt, atol=1e-10, reactor_type=2)
-        assert_rk64_parity(a.rY, a.T, b.rY, b.T)
+        # the enthalpy form is far more sensitive to rounding than the energy form: the SAME reference C code built with
+        # -mfma differs from its strict build by 1.7e-8 (species) / 1e-9 (T) on these drm19 states, with identical step
+        # counts (tools/fma_spread_rk64.py; energy form: 1.2e-10 / 6e-12).  The GPU contracts to FMA: bar 1e-7.
+        assert_rk64_parity(a.rY, a.T, b.rY, b.T, rtol=1e-7)
+        assert np.array_equal(a.rE, b.rE) and np.mean(a.FC == b.FC) >= 0.9
         r.close()
