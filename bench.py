@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--atol", type=float, default=1e-10)
     ap.add_argument("--max-order", type=int, default=4)
     ap.add_argument("--dt", type=float, default=1e-6)
+    ap.add_argument("--states", default="reacteval", choices=["reacteval", "pmf"],
+                    help="reacteval: ReactEval initialize_data (BASELINE configs); pmf: flame-table samples, unrelated neighbours "
+                         "(tests/golden/pmf_states_<mech>.npz, SURVEY 8(d) set B: the divergent workload)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -53,8 +56,9 @@ def workload_name(a):
     tol = "rtol=%g atol=%g max_order=%d denseAJ_direct" % (a.rtol, a.atol, a.max_order)
     if a.reactor == "ReactorRK64":
         tol = "atol=%g" % a.atol
-    return "%d^3 synthetic %s states (ReactEval initialize_data), %s, dt=%g s, %s" % (
-        a.n, a.mech, a.reactor, a.dt, tol)
+    src = "ReactEval initialize_data" if a.states == "reacteval" else \
+        "2048 seeded samples of the reference PMF flame table scattered over the box: neighbouring cells unrelated"
+    return "%d^3 synthetic %s states (%s), %s, dt=%g s, %s" % (a.n, a.mech, src, a.reactor, a.dt, tol)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -62,13 +66,18 @@ def workload_name(a):
 # ------------------------------------------------------------------------------------------------
 def _cpu_worker(args):
     """One process = one host core: react `ncells_j` j-lines of the workload with the CPU implementation."""
-    kind, mech, reactor, n, j_lo, j_hi, reps, rtol, atol, max_order, dt = args
+    kind, mech, reactor, n, j_lo, j_hi, reps, rtol, atol, max_order, dt, states = args
     devnull = os.open(os.devnull, os.O_WRONLY)
     os.dup2(devnull, 1)  # the reference prints banners on stdout
     from oracle.pyoracle import Oracle, Reference, reacteval_states
     lib = Reference(mech) if kind == "reference" else Oracle(mech)
-    full = reacteval_states(lib, (1, n, 1))  # one cell per j: the states depend on j only
     import numpy as np
+    if states == "pmf":
+        from oracle.pyoracle import BoxState
+        z = np.load(os.path.join(ROOT, "tests", "golden", "pmf_states_%s.npz" % mech))
+        full = BoxState(z["rY"].copy(), z["T"].copy(), z["rE"].copy(), np.zeros_like(z["rY"]), np.zeros_like(z["T"]))
+    else:
+        full = reacteval_states(lib, (1, n, 1))  # one cell per j: the states depend on j only
     idx = np.arange(j_lo, j_hi)
     t0 = time.perf_counter()
     cells = 0
@@ -93,10 +102,11 @@ def cpu_throughput(a, seconds):
     # calibrate on one j-sweep in one process
     ctx = mp.get_context("spawn")
     with ctx.Pool(1) as p:
-        c0, t0 = p.map(_cpu_worker, [(kind, a.mech, a.reactor, n, 0, n, 1, a.rtol, a.atol, a.max_order, a.dt)])[0]
+        ns = n if a.states == "reacteval" else 2048
+        c0, t0 = p.map(_cpu_worker, [(kind, a.mech, a.reactor, n, 0, ns, 1, a.rtol, a.atol, a.max_order, a.dt, a.states)])[0]
     per_sweep = max(t0, 1e-6)
     reps = max(1, int(seconds / per_sweep))
-    jobs = [(kind, a.mech, a.reactor, n, 0, n, reps, a.rtol, a.atol, a.max_order, a.dt) for _ in range(cores)]
+    jobs = [(kind, a.mech, a.reactor, n, 0, ns, reps, a.rtol, a.atol, a.max_order, a.dt, a.states) for _ in range(cores)]
     t_start = time.perf_counter()
     with ctx.Pool(cores) as p:
         res = p.map(_cpu_worker, jobs)
@@ -105,8 +115,8 @@ def cpu_throughput(a, seconds):
     tmax = max(r[1] for r in res)
     return {
         "value": cells / tmax, "unit": UNIT, "cores": cores, "kind": kind,
-        "sample": "%d processes x %d sweeps of the %d distinct cell states of the workload (states depend on j only) "
-                  "= %d cell integrations in %.1f s" % (cores, reps, n, cells, wall),
+        "sample": "%d processes x %d sweeps of the %d distinct cell states of the workload "
+                  "= %d cell integrations in %.1f s" % (cores, reps, ns, cells, wall),
         "per_core": cells / tmax / cores,
     }
 
@@ -186,7 +196,7 @@ def run_b200(a):
     # ---- synthetic states, built on the host by the generator's own EOS tables (no oracle involved):
     # ReactEval's initialize_data needs X->Y and (P,Y,T)->(rho,e); compute them with the mechanism JSON.
     N, n = gen.op_counts(a.mech)["N"], a.n
-    rY_h, T_h, rE_h = synth_states(a.mech, n)
+    rY_h, T_h, rE_h = synth_states(a.mech, n) if a.states == "reacteval" else pmf_states(a.mech, n)
     ncell = n ** 3
 
     def fab(t, ncomp):
@@ -329,6 +339,16 @@ def run_b200(a):
     r.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def pmf_states(mech, n):
+    """Set B: the 2048 flame-table samples of tests/golden/pmf_states_<mech>.npz scattered over an n^3 box by
+    a multiplicative hash of the cell index, so that the 32 cells of a warp are unrelated flame positions."""
+    import numpy as np
+    z = np.load(os.path.join(ROOT, "tests", "golden", "pmf_states_%s.npz" % mech))
+    idx = (np.arange(n ** 3, dtype=np.uint64) * np.uint64(2654435761) >> np.uint64(7)) % np.uint64(z["T"].shape[0])
+    idx = idx.astype(np.int64)
+    return z["rY"][:, idx].reshape(-1).copy(), z["T"][idx].copy(), z["rE"][idx].copy()
 
 
 def ncu_traffic(kernel, ncell):

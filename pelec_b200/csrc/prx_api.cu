@@ -9,6 +9,8 @@
 
 #include "prx_kernels.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 using namespace prx;
 
 struct prx_handle
@@ -307,6 +309,8 @@ int prx_create(const prx_config* cfg, prx_handle** out)
   h->sched.bdf_variant = env_int("PRX_BDF_VARIANT", -1);
   h->sched.max_warps_per_sm = env_int("PRX_MAX_WARPS_PER_SM", 0);
   h->sched.coop_a_global = env_int("PRX_COOP_A_GLOBAL", -1);
+  h->sched.refill_min = env_int("PRX_REFILL_MIN", -1);
+  h->sched.sort_cells = env_int("PRX_SORT_CELLS", 1);
   h->sched.lu_defer_block = env_int("PRX_LU_DEFER_BLOCK", 0);
   h->sched.lu_defer_max_age = env_int("PRX_LU_DEFER_AGE", 6);
   h->sched.block_warps = env_int("PRX_BLOCK_WARPS", 0); // 0: kernel default (gen-1: both block barriers; hot/cold: single warps)
@@ -319,6 +323,16 @@ int prx_create(const prx_config* cfg, prx_handle** out)
   h->keep_last_steps = false;
   h->err[0] = 0;
   DeviceGuard g(dev);
+  {
+    // the per-call scratch (cell order, Jacobian slots, cold columns) comes from the stream-ordered pool: keep the pool's
+    // memory across synchronisations instead of returning it to the driver after every call
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess && pool != nullptr) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   if (cudaMalloc(&h->d_stats, sizeof(DevStats)) != cudaSuccess ||
       cudaMalloc(&h->d_queues, sizeof(int) * h->n_queues) != cudaSuccess ||
       cudaMemset(h->d_stats, 0, sizeof(DevStats)) != cudaSuccess ||
@@ -378,6 +392,67 @@ int prx_set_typ_vals(prx_handle* h, const double* typ, int n)
 
 const char* prx_last_error(const prx_handle* h) { return h ? h->err : "null handle"; }
 
+// ---- cell ordering -----------------------------------------------------------------------------
+// The kernels draw cells from a work queue; handing them out SORTED BY TEMPERATURE puts thermochemically
+// similar cells (similar step counts, Newton iterations and Jacobian refreshes) into the same warp, which is
+// what keeps one-cell-per-thread integrators converged on flame-like fields where neighbours in index space
+// are unrelated (bench.py --states pmf: 319 -> see profiles/README.md).  Each cell's arithmetic does not depend
+// on the order.  Key = T as float; stable radix sort (cub), so equal temperatures keep index order.
+__global__ void order_keys_kernel(const BoxArgs a, const int neq, float* __restrict__ keys, int* __restrict__ idx)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.ncells) {
+    return;
+  }
+  double T;
+  if (a.layout == LAYOUT_ARRAY4) {
+    const int i = c % a.len[0];
+    const int r = c / a.len[0];
+    const int j = r % a.len[1];
+    const int k = r / a.len[1];
+    T = a.T.p[(long long)i + (long long)j * a.T.js + (long long)k * a.T.ks];
+  } else {
+    T = a.y[(long long)c * neq + (neq - 1)];
+  }
+  keys[c] = (float)T;
+  idx[c] = c;
+}
+
+// returns a stream-ordered allocation holding [order | scratch]; the caller frees it (cudaFreeAsync) after the launch
+static cudaError_t build_order(const BoxArgs& a, int neq, cudaStream_t stream, void** block_out, const int** order_out)
+{
+  const size_t n = (size_t)a.ncells;
+  size_t temp_bytes = 0;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(
+    nullptr, temp_bytes, (const float*)nullptr, (float*)nullptr, (const int*)nullptr, (int*)nullptr, (int)n, 0, 32, stream);
+  if (e != cudaSuccess) {
+    return e;
+  }
+  const size_t off_keys_in = n * sizeof(int), off_keys_out = off_keys_in + n * sizeof(float),
+               off_idx_in = off_keys_out + n * sizeof(float), off_temp = (off_idx_in + n * sizeof(int) + 255) & ~(size_t)255;
+  char* block = nullptr;
+  e = cudaMallocAsync((void**)&block, off_temp + temp_bytes, stream);
+  if (e != cudaSuccess) {
+    return e;
+  }
+  int* order = (int*)block;
+  float* keys_in = (float*)(block + off_keys_in);
+  float* keys_out = (float*)(block + off_keys_out);
+  int* idx_in = (int*)(block + off_idx_in);
+  order_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a, neq, keys_in, idx_in);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) {
+    e = cub::DeviceRadixSort::SortPairs(block + off_temp, temp_bytes, keys_in, keys_out, idx_in, order, (int)n, 0, 32, stream);
+  }
+  if (e != cudaSuccess) {
+    cudaFreeAsync(block, stream);
+    return e;
+  }
+  *block_out = block;
+  *order_out = order;
+  return cudaSuccess;
+}
+
 static int react_args(prx_handle* h, const BoxArgs& a, cudaStream_t stream)
 {
   DeviceGuard g(h->device);
@@ -388,10 +463,26 @@ static int react_args(prx_handle* h, const BoxArgs& a, cudaStream_t stream)
   }
   h->last_ncells += a.ncells;
   cudaError_t e;
+  BoxArgs b = a;
+  void* order_block = nullptr;
+  b.order = nullptr;
+  if (h->sched.sort_cells && a.ncells >= 4096) {
+    e = build_order(a, h->ops->num_species + 1, stream, &order_block, &b.order);
+    if (e != cudaSuccess) {
+      return fail(h, PRX_ERR_CUDA, "cell ordering", e);
+    }
+  }
+  SchedParams sp = h->sched;
+  if (sp.refill_min < 0) { // default: batch the refills of a warp only when the cells arrive unsorted
+    sp.refill_min = (b.order != nullptr) ? 1 : 16;
+  }
   if (h->cfg.reactor_kind == PRX_REACTOR_RK64) {
-    e = h->ops->launch_rk64(a, h->cfg, next_queue(h), h->d_stats, stream);
+    e = h->ops->launch_rk64(b, h->cfg, next_queue(h), h->d_stats, stream);
   } else {
-    e = h->ops->launch_bdf(a, h->cfg, h->typ_vals.data(), next_queue(h), h->d_stats, h->sched, stream);
+    e = h->ops->launch_bdf(b, h->cfg, h->typ_vals.data(), next_queue(h), h->d_stats, sp, stream);
+  }
+  if (order_block != nullptr) {
+    cudaFreeAsync(order_block, stream); // stream-ordered: released after the integrator kernel
   }
   if (e != cudaSuccess) {
     return fail(h, PRX_ERR_CUDA, "kernel launch", e);

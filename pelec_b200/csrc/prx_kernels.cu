@@ -247,7 +247,10 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(rk64_kernel_
   int req = REQ_NONE;
   LaneStats ls = {};
   for (;;) {
-    const int got = fetch_cell((cell < 0) && !exhausted, queue, a.ncells);
+    int got = fetch_cell((cell < 0) && !exhausted, queue, a.ncells);
+    if (got >= 0 && a.order != nullptr) {
+      got = a.order[got]; // cells handed out in sorted order (see prx_api.cu build_order)
+    }
     if (got == -2) {
       exhausted = true;
     } else if (got >= 0) {
@@ -318,7 +321,21 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
   LaneStats ls = {};
   for (;;) {
     // ---- (1) refill ----
-    const int got = fetch_cell((cell < 0) && !exhausted, queue, a.ncells);
+    // Refill in batches: with unrelated neighbouring cells a lane that restarts alone evaluates its first Jacobian and
+    // factorisation alone (1/32 lane efficiency); holding idle lanes back until refill_min of them are free makes the
+    // new cells start - and ask for their Jacobians - together.
+    bool want = (cell < 0) && !exhausted;
+    if (sp.refill_min > 1) {
+      const unsigned m_want = __ballot_sync(FULL, want);
+      const unsigned m_busy = __ballot_sync(FULL, cell >= 0);
+      if (m_busy != 0u && __popc(m_want) < sp.refill_min) {
+        want = false;
+      }
+    }
+    int got = fetch_cell(want, queue, a.ncells);
+    if (got >= 0 && a.order != nullptr) {
+      got = a.order[got]; // cells handed out in sorted order (see prx_api.cu build_order)
+    }
     if (got == -2) {
       exhausted = true;
     } else if (got >= 0) {
@@ -483,7 +500,10 @@ __global__ void __launch_bounds__(32) PRX_CAT(bdf2_kernel_, PRX_MECH_SUFFIX)(
   pc.array4_semantics = 0; // the initial T solve is done here with the table-driven Newton loop
   for (;;) {
     // ---- (1) refill ----
-    const int got = fetch_cell((cell < 0) && !exhausted, queue, a.ncells);
+    int got = fetch_cell((cell < 0) && !exhausted, queue, a.ncells);
+    if (got >= 0 && a.order != nullptr) {
+      got = a.order[got]; // cells handed out in sorted order (see prx_api.cu build_order)
+    }
     if (got == -2) {
       exhausted = true;
     } else if (got >= 0) {
@@ -688,7 +708,10 @@ __global__ void __launch_bounds__(128, PRX_BDF3_MINBLOCKS / 4) PRX_CAT(bdf3_kern
   pc.array4_semantics = 0; // the initial T solve is done here with the table-driven Newton loop
   for (;;) {
     // ---- (1) refill ----
-    const int got = fetch_cell((cell < 0) && !exhausted, queue, a.ncells);
+    int got = fetch_cell((cell < 0) && !exhausted, queue, a.ncells);
+    if (got >= 0 && a.order != nullptr) {
+      got = a.order[got]; // cells handed out in sorted order (see prx_api.cu build_order)
+    }
     if (got == -2) {
       exhausted = true;
     } else if (got >= 0) {
@@ -974,6 +997,9 @@ __global__ void __launch_bounds__(32, PRX_COOP_MINBLOCKS) PRX_CAT(bdfc_kernel_, 
   for (;;) {
     // ---- (1) refill: the group leaders draw cell indices (one atomic per warp), then broadcast ----
     int got = fetch_cell((cell < 0) && !exhausted && (g.gl == 0), queue, a.ncells);
+    if (got >= 0 && a.order != nullptr) {
+      got = a.order[got];
+    }
     got = __shfl_sync(FULL, got, (int)(lane & ~(unsigned)(G - 1)));
     if (got == -2) {
       exhausted = true;

@@ -39,6 +39,7 @@ struct BoxArgs
   const double* esrc;
   double* fc;
   double dt, time;
+  const int* order; // optional: queue position -> cell index (cells sorted by temperature), nullptr = identity
 };
 
 // device-side counters (unsigned long long so that atomicAdd applies)
@@ -61,6 +62,8 @@ struct SchedParams
   int coop_a_global;    // cooperative kernel: Newton matrix in global memory (1), shared memory (0), by size (-1)
   int lu_defer_block;   // gen-1 kernel: percent of the block's threads that must hold a Jacobian/LU request before they are served (0: off)
   int lu_defer_max_age; // ... but never wait longer than this many iterations
+  int refill_min;       // gen-1 kernel: idle lanes of a warp wait until this many are free before they take new cells
+  int sort_cells;       // hand cells out sorted by temperature (1) or in index order (0)
   int block_warps;      // warps per block of the hot/cold kernel (1: independent warps; 2-4: phase-aligned by a block barrier)
 };
 

@@ -358,3 +358,36 @@ def test_enthalpy_form_matches_oracle(mech):
         assert_rk64_parity(a.rY, a.T, b.rY, b.T, rtol=1e-7)
         assert np.array_equal(a.rE, b.rE) and np.mean(a.FC == b.FC) >= 0.9
         r.close()
+
+
+@pytest.mark.parametrize("mname", ["LiDryer", "drm19"])
+def test_flame_table_states_divergent_warps(mname):
+    """Set B of SURVEY 8(d): 2048 states sampled from the reference's premixed-flame table (cold reactants at 298 K,
+    the reaction zone, hot products), in seeded random order, so that the cells of a warp take very different numbers of
+    steps.  The default kernels against the oracle, cell for cell, plus the work counters."""
+    import os
+    from util import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "pmf_states_%s.npz" % mname))
+    orc = Oracle(mname)
+    n = z["T"].shape[0]
+    base = BoxState(z["rY"].copy(), z["T"].copy(), z["rE"].copy(), np.zeros_like(z["rY"]), np.zeros(n))
+    kw = CVODE_SETTINGS[1]
+    a, b = base.copy(), base.copy()
+    r = make_reactor("ReactorCvode", mname, **cvode_parm(kw))
+    react_host(r, a, 1e-6)
+    orc.react_cvode(b, 1e-6, **kw)
+    assert_cvode_parity(a.rY, a.T, b.rY, b.T, kw["atol"], kw["rtol"])
+    assert abs(a.FC.sum() - b.FC.sum()) <= 0.05 * b.FC.sum() and a.FC.max() > 2 * np.median(a.FC)  # really divergent
+    st = r.stats()
+    assert st["cells"] == n and st["n_failed"] == 0
+    r.close()
+    a, b = base.copy(), base.copy()
+    r = make_reactor("ReactorRK64", mname, ode__atol=1e-10)
+    react_host(r, a, 1e-6)
+    orc.react_rk64(b, 1e-6, atol=1e-10)
+    # drm19 on these states: the reference's own C code built with -mfma differs from its strict build by 2.9e-7 (species)
+    # / 3.1e-9 (T) and takes a different number of steps in 0.5 % of the cells (controller branches flip on the last bit);
+    # LiDryer: 3e-15, identical step counts.  Measured with the recipe of tools/fma_spread_rk64.py on this fixture.
+    assert_rk64_parity(a.rY, a.T, b.rY, b.T, rtol=2e-6 if mname == "drm19" else 1e-10)
+    assert np.mean(a.FC == b.FC) >= 0.9
+    r.close()

@@ -19,8 +19,11 @@ timeout 600 python bench.py --mech drm19 --n 64 --no-cpu-baseline 2>>gpurun_out/
 timeout 900 python bench.py --mech drm19 --n 128 --steps 3 --no-cpu-baseline 2>>gpurun_out/${TAG}_bench.err > gpurun_out/${TAG}_bench_drm19_cvode_128.json
 timeout 900 python bench.py --mech dodecane_lu --n 32 --steps 3 --no-cpu-baseline 2>>gpurun_out/${TAG}_bench.err > gpurun_out/${TAG}_bench_dodecane_cvode_32.json
 timeout 600 python bench.py --rtol 1e-6 --atol 1e-10 --max-order 2 --no-cpu-baseline 2>>gpurun_out/${TAG}_bench.err > gpurun_out/${TAG}_bench_lidryer_cvode_128_pelec_tols.json
-PRX_BLOCK_WARPS=1 timeout 600 python bench.py --steps 3 --no-cpu-baseline 2>>gpurun_out/${TAG}_bench.err > gpurun_out/${TAG}_bench_x_lidryer_no_barrier.json
-PRX_BLOCK_WARPS=1 timeout 600 python bench.py --steps 3 --mech drm19 --n 64 --no-cpu-baseline 2>>gpurun_out/${TAG}_bench.err > gpurun_out/${TAG}_bench_x_drm19_no_barrier.json
+PRX_SORT_CELLS=0 timeout 600 python bench.py --steps 3 --no-cpu-baseline 2>>gpurun_out/${TAG}_bench.err > gpurun_out/${TAG}_bench_x_lidryer_unsorted.json
+timeout 900 python bench.py --states pmf --cpu-seconds 10 2>>gpurun_out/${TAG}_bench.err > gpurun_out/${TAG}_bench_lidryer_cvode_128_pmf_states.json
+PRX_SORT_CELLS=0 timeout 600 python bench.py --states pmf --steps 3 --no-cpu-baseline 2>>gpurun_out/${TAG}_bench.err > gpurun_out/${TAG}_bench_x_lidryer_pmf_states_unsorted.json
+timeout 600 python bench.py --states pmf --mech drm19 --n 64 --no-cpu-baseline 2>>gpurun_out/${TAG}_bench.err > gpurun_out/${TAG}_bench_drm19_cvode_64_pmf_states.json
+timeout 600 python bench.py --states pmf --reactor ReactorRK64 --no-cpu-baseline 2>>gpurun_out/${TAG}_bench.err > gpurun_out/${TAG}_bench_lidryer_rk64_128_pmf_states.json
 python - <<PY
 import json, glob
 for f in sorted(glob.glob("gpurun_out/${TAG}_bench_*.json")):
