@@ -316,7 +316,8 @@ def run_b200(a):
                              % ((2 * N + 6) * 8 * ncell / 1e6)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "prx_react_box_host (C ABI, pinned host buffers)"},
-            "gpu_launches": a.steps,
+            # per step: the integrator kernel + the key kernel of the cell ordering (the radix sort itself is cub)
+            "gpu_launches": a.steps * (2 if (ncell >= 4096 and os.environ.get("PRX_SORT_CELLS", "1") != "0") else 1),
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
                 "frac": achieved / peak.value if peak.value > 0 else None,
