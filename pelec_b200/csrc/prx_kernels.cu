@@ -309,6 +309,21 @@ __device__ __forceinline__ double* bdf_vec(BdfCell& s, const int sel)
 // 16k-line dodecane_lu Jacobian costs six minutes of compile time): large ones use the cooperative kernel
 #define PRX_HAVE_BDF1 (PRX_NUM_SPECIES <= 32)
 #if PRX_HAVE_BDF1
+#ifndef PRX_OUTLINE
+#define PRX_OUTLINE 0 // bit 0: Jacobian out of line, bit 1: RHS out of line (separate register allocation, fewer spills in the loop)
+#endif
+#if PRX_OUTLINE & 1
+__device__ __noinline__ void jac_outline(const int reactor_type, const double* y, double* J)
+{
+  jac_analytic(reactor_type, y, J, [J](const int row, const int col, const double v) { J[col * NEQ + row] = v; });
+}
+#endif
+#if PRX_OUTLINE & 2
+__device__ __noinline__ void rhs_outline(const double t, const int reactor_type, const double* y, double* ydot, const CellSrc* c)
+{
+  rhs(t, reactor_type, y, ydot, *c);
+}
+#endif
 __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_, PRX_MECH_SUFFIX)(
   const BoxArgs a, const BdfParams p, const SchedParams sp, int* __restrict__ queue,
   DevStats* __restrict__ stats)
@@ -371,9 +386,13 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
       }
       if (req == REQ_JAC) {
         double* J = s.savedJ();
+#if PRX_OUTLINE & 1
+        jac_outline(p.reactor_type, s.y(), J);
+#else
         jac_analytic(p.reactor_type, s.y(), J, [J](const int row, const int col, const double v) {
           J[col * NEQ + row] = v;
         });
+#endif
         req = REQ_NONE;
       }
       if (req == REQ_LU) {
@@ -413,7 +432,11 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
     const unsigned m_jac = __ballot_sync(FULL, req == REQ_JAC && slow_ok);
     const unsigned m_lu = __ballot_sync(FULL, req == REQ_LU && slow_ok);
     if (req == REQ_RHS) {
+#if PRX_OUTLINE & 2
+      rhs_outline(s.t_eval, p.reactor_type, s.vec(s.in_sel), s.vec(s.out_sel), &s.src);
+#else
       rhs(s.t_eval, p.reactor_type, s.vec(s.in_sel), s.vec(s.out_sel), s.src);
+#endif
       req = REQ_NONE;
     }
 #if !PRX_INLINE_SLOW
