@@ -593,11 +593,13 @@ int prx_react_box_host(
   double* d_rEsrc = d_rE + nc;
   double* d_FC = d_rEsrc + nc;
   int* d_mask = reinterpret_cast<int*>(d_FC + nc);
-  // Slab pipeline: the box is cut along k into up to 4 slabs; slab s+1 is copied in while slab s reacts and slab
+  // Slab pipeline: the box is cut along k into slabs (PRX_HOST_SLABS, default 2: measured best of 1..12); slab s+1 is copied in while slab s reacts and slab
   // s-1 is copied out (three streams, full-duplex PCIe).  Every array is SoA with component stride nc, so one slab
   // of one array is a 2-D copy: rows = components (pitch nc), row length = the slab's cells.
   const long long plane = (long long)nx * ny;
-  int nslab = (nz >= 8 && nc >= (1LL << 18)) ? 4 : 1;
+  int nslab = (nz >= 8 && nc >= (1LL << 18)) ? env_int("PRX_HOST_SLABS", 2) : 1;
+  nslab = nslab < 1 ? 1 : (nslab > 16 ? 16 : nslab);
+  nslab = nslab > nz ? nz : nslab;
   auto mk = [&](double* p, int ncomp) {
     prx_array4 a;
     a.p = p;
@@ -623,7 +625,7 @@ int prx_react_box_host(
   a_mask.end[1] = ny;
   a_mask.end[2] = nz;
   a_mask.ncomp = 1;
-  cudaEvent_t ev_in[4], ev_done[4];
+  cudaEvent_t ev_in[16], ev_done[16];
   for (int sidx = 0; sidx < nslab; sidx++) {
     PRX_CUDA(h, cudaEventCreateWithFlags(&ev_in[sidx], cudaEventDisableTiming));
     PRX_CUDA(h, cudaEventCreateWithFlags(&ev_done[sidx], cudaEventDisableTiming));
