@@ -34,6 +34,9 @@
 #ifndef PRX_INLINE_SLOW
 #define PRX_INLINE_SLOW 0
 #endif
+#ifndef PRX_PREFETCH_SRC
+#define PRX_PREFETCH_SRC 0
+#endif
 #ifndef PRX_BDF_DEFAULT_VARIANT
 #define PRX_BDF_DEFAULT_VARIANT 0
 #endif
@@ -432,6 +435,14 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
     const unsigned m_jac = __ballot_sync(FULL, req == REQ_JAC && slow_ok);
     const unsigned m_lu = __ballot_sync(FULL, req == REQ_LU && slow_ok);
     if (req == REQ_RHS) {
+#if PRX_PREFETCH_SRC
+      // the external species source is read at the very end of the RHS, from local memory that has usually left L1
+      // by then (ncu r01k: 6 % of the stall samples on that line): start the fetch now
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        asm volatile("prefetch.L1 [%0];" ::"l"(&s.src.rYsrc[k]));
+      }
+#endif
 #if PRX_OUTLINE & 2
       rhs_outline(s.t_eval, p.reactor_type, s.vec(s.in_sel), s.vec(s.out_sel), &s.src);
 #else
