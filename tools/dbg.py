@@ -1,3 +1,6 @@
+"""TEST TOOLING (not product): one small ReactorCvode call through the C ABI with progress prints, checked against the
+oracle - used by the tools/gpu_session*.sh scripts to localise crashes and to spot-check parity of A/B builds
+(PRX_LIB_PATH, PRX_BDF_VARIANT).  usage: python tools/dbg.py [mechanism]"""
 import sys, os, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def P(*a):
