@@ -3,7 +3,9 @@
 // CPU compute path: if there is no CUDA device, prx_create fails.
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -22,7 +24,8 @@ struct prx_handle
   DevStats* d_stats;
   int* d_queues; // ring of work-queue counters: one per in-flight launch
   int n_queues;
-  int q_next;
+  std::atomic<unsigned> q_next; // several host threads may launch through one handle (different streams)
+  std::mutex host_mutex;        // the *_host calls share one staging buffer: serialised per handle
   SchedParams sched;
   long long last_ncells;
   // staging for the *_host convenience calls
@@ -108,8 +111,7 @@ bool view_of(const prx_array4* a, const int lo[3], int need_comp, ArrView* v)
 
 int* next_queue(prx_handle* h)
 {
-  int* q = h->d_queues + h->q_next;
-  h->q_next = (h->q_next + 1) % h->n_queues;
+  int* q = h->d_queues + (h->q_next.fetch_add(1u) % (unsigned)h->n_queues);
   return q;
 }
 
@@ -303,7 +305,7 @@ int prx_create(const prx_config* cfg, prx_handle** out)
   h->d_stats = nullptr;
   h->d_queues = nullptr;
   h->n_queues = 256;
-  h->q_next = 0;
+  h->q_next.store(0u);
   h->sched.jac_defer_min_lanes = env_int("PRX_JAC_DEFER", 1);
   h->sched.lu_defer_min_lanes = env_int("PRX_LU_DEFER", 1);
   h->sched.bdf_variant = env_int("PRX_BDF_VARIANT", -1);
@@ -576,6 +578,7 @@ int prx_react_box_host(
   if (rY == nullptr || rYsrc == nullptr || T == nullptr || rE == nullptr || rEsrc == nullptr || FC == nullptr) {
     return fail(h, PRX_ERR_BAD_ARG, "prx_react_box_host: null pointer");
   }
+  std::lock_guard<std::mutex> host_lock(h->host_mutex);
   DeviceGuard g(h->device);
   const int N = h->ops->num_species;
   // device staging: [rY N][rYsrc N][T][rE][rEsrc][FC] doubles + mask ints
@@ -774,6 +777,7 @@ int prx_react_flat_host(
   if (ncells == 0) {
     return PRX_OK;
   }
+  std::lock_guard<std::mutex> host_lock(h->host_mutex);
   if (y == nullptr || ysrc == nullptr || e == nullptr || esrc == nullptr) {
     return fail(h, PRX_ERR_BAD_ARG, "prx_react_flat_host: null pointer");
   }

@@ -391,3 +391,57 @@ def test_flame_table_states_divergent_warps(mname):
     assert_rk64_parity(a.rY, a.T, b.rY, b.T, rtol=2e-6 if mname == "drm19" else 1e-10)
     assert np.mean(a.FC == b.FC) >= 0.9
     r.close()
+
+
+def test_two_host_threads_share_one_reactor():
+    """PeleC's CPU builds call react() concurrently from OpenMP threads with ONE reactor object (React.cpp:133-138) and
+    its GPU builds round-robin several streams: two host threads, two streams, one handle, eight boxes each - every box
+    must come out exactly as in a single-threaded run (the per-launch work queues are handed out atomically)."""
+    import threading
+    mech = "LiDryer"
+    orc = Oracle(mech)
+    N = orc.N
+    n = 24  # 13824 cells per box: sorted work queue, several waves
+    st = reacteval_states(orc, (n, n, n))
+    dev = torch.device("cuda:0")
+    r = make_reactor("ReactorRK64", mech, ode__atol=1e-10)
+
+    def fab(a, ncomp):
+        return torch.from_numpy(a.reshape(ncomp, n, n, n).copy()).to(dev)
+
+    def make_box():
+        return dict(rY=fab(st.rY, N), rYs=fab(st.rYsrc, N), T=fab(st.T, 1), rE=fab(st.rE, 1), rEs=fab(st.rEsrc, 1),
+                    FC=torch.zeros((1, n, n, n), dtype=torch.float64, device=dev),
+                    mask=torch.ones((1, n, n, n), dtype=torch.int32, device=dev))
+
+    def react(b, stream):
+        r.react(Box((0, 0, 0), (n - 1, n - 1, n - 1)), Array4(b["rY"]), Array4(b["rYs"]), Array4(b["T"]), Array4(b["rE"]),
+                Array4(b["rEs"]), Array4(b["FC"]), Array4(b["mask"]), 1e-6, 0.0, stream=stream.cuda_stream)
+
+    ref = make_box()
+    react(ref, torch.cuda.current_stream(dev))
+    torch.cuda.synchronize()
+    boxes = [[make_box() for _ in range(8)] for _ in range(2)]
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    torch.cuda.synchronize()
+    errs = []
+
+    def worker(t):
+        try:
+            for b in boxes[t]:
+                react(b, streams[t])
+            streams[t].synchronize()
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    torch.cuda.synchronize()
+    assert not errs
+    for t in range(2):
+        for b in boxes[t]:
+            assert torch.equal(b["rY"], ref["rY"]) and torch.equal(b["T"], ref["T"]) and torch.equal(b["FC"], ref["FC"])
+    assert r.stats()["cells"] == 17 * n ** 3
+    r.close()
