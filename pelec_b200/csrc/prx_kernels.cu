@@ -1497,7 +1497,14 @@ cudaError_t launch_bdf(
 #if PRX_HAVE_BDF1
   auto kern = PRX_CAT(bdf_kernel_, PRX_MECH_SUFFIX);
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1); // state lives in L1-cached local memory
-  const int grid = persistent_grid((const void*)kern, a.ncells);
+  int grid = persistent_grid((const void*)kern, a.ncells);
+  if (sp.max_warps_per_sm > 0) { // optional cap on resident warps (fewer resident cells: smaller L2 footprint)
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sp.max_warps_per_sm / (PRX_BLOCK / 32) > 0 ? sp.max_warps_per_sm / (PRX_BLOCK / 32) : 1;
+    grid = grid < sms * blocks ? grid : sms * blocks;
+  }
   cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(int), stream);
   if (e != cudaSuccess) {
     return e;
