@@ -23,6 +23,12 @@
 #include "prx_coop.cuh"
 #include "prx_kernels.cuh"
 
+#ifndef PRX_RK_BLOCK // block shape of the RK64 kernel (its register appetite differs from the BDF kernel's)
+#define PRX_RK_BLOCK PRX_BLOCK
+#endif
+#ifndef PRX_RK_MINBLOCKS
+#define PRX_RK_MINBLOCKS PRX_MINBLOCKS
+#endif
 #ifndef PRX_BLOCK
 #define PRX_BLOCK 128
 #endif
@@ -241,7 +247,7 @@ __device__ __forceinline__ void store_cell(
 // =====================================================================================
 // RK64 kernel
 // =====================================================================================
-__global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(rk64_kernel_, PRX_MECH_SUFFIX)(
+__global__ void __launch_bounds__(PRX_RK_BLOCK, PRX_RK_MINBLOCKS) PRX_CAT(rk64_kernel_, PRX_MECH_SUFFIX)(
   const BoxArgs a, const Rk64Params p, int* __restrict__ queue, DevStats* __restrict__ stats)
 {
   Rk64Cell s;
@@ -1404,16 +1410,16 @@ cudaError_t launch_unflatten(
 // =====================================================================================
 // launchers
 // =====================================================================================
-int persistent_grid(const void* kernel, const int ncells)
+int persistent_grid(const void* kernel, const int ncells, const int block = PRX_BLOCK)
 {
   int dev = 0, sms = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, PRX_BLOCK, 0) != cudaSuccess || per_sm < 1) {
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) {
     per_sm = 1;
   }
   long long grid = (long long)sms * per_sm; // a multiple of the SM count: one full wave, persistent
-  const long long needed = ((long long)ncells + PRX_BLOCK - 1) / PRX_BLOCK;
+  const long long needed = ((long long)ncells + block - 1) / block;
   if (needed < grid) {
     grid = needed;
   }
@@ -1433,12 +1439,12 @@ cudaError_t launch_rk64(const BoxArgs& a, const prx_config& cfg, int* queue, Dev
   p.nsub_max = cfg.rk64_nsubsteps_max;
   p.array4_semantics = (a.layout == LAYOUT_ARRAY4);
   auto kern = PRX_CAT(rk64_kernel_, PRX_MECH_SUFFIX);
-  const int grid = persistent_grid((const void*)kern, a.ncells);
+  const int grid = persistent_grid((const void*)kern, a.ncells, PRX_RK_BLOCK);
   cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(int), stream);
   if (e != cudaSuccess) {
     return e;
   }
-  kern<<<grid, PRX_BLOCK, 0, stream>>>(a, p, queue, stats);
+  kern<<<grid, PRX_RK_BLOCK, 0, stream>>>(a, p, queue, stats);
   return cudaGetLastError();
 }
 
