@@ -144,7 +144,12 @@ PRX_API int prx_react_box(
 /* ---- ReactorBase::react, flat version (ReactorBase.H:42-54), DEVICE pointers ----
  * y [ncells*(N+1)] YCOrder (cell-major, T last), ysrc [ncells*N], e [ncells], esrc [ncells].
  * Reference semantics of the 1-D call: T is taken from y (no initial REY2T) and the
- * integrated T is returned (ReactorRK64.cpp:82-96,140-143). fc may be NULL. */
+ * integrated T is returned (ReactorRK64.cpp:82-96,140-143). fc may be NULL.
+ * ReactorCvode difference, by design: the reference's 1-D CVODE react (ReactorCvode.cpp:1491-1689) integrates the ncells
+ * cells of ONE call as one coupled ODE system (one step size, one WRMS norm over all cells); this library integrates every
+ * cell as its own system - the semantics of the reference's Array4 CPU path (ReactorCvode.cpp:1383-1464) - so results
+ * coincide with the reference's for ncells = 1 and agree within the integrator tolerance otherwise.  The value the
+ * reference returns from this call (nfe + nfeLS) is prx_last_react_return(): the largest per-cell count of the call. */
 PRX_API int prx_react_flat(
   prx_handle* h, double* y, const double* ysrc, double* e, const double* esrc, double* fc,
   double dt, double time, int ncells, void* cuda_stream);

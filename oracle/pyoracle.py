@@ -267,6 +267,19 @@ class Reference:
         finally:
             self.lib.peleref_reactor_destroy(h)
 
+    def react_flat(self, key, y, ysrc, e, esrc, dt, time=0.0, reactor_type=1):
+        """The reference's 1-D react(Real* rY_in, rYsrc_in, rX_in, rX_src_in, dt, time, ncells) (ReactorBase.H:42-54):
+        y [ncells, N+1] (rhoY, T) in/out, ysrc [ncells, N], e [ncells] in/out, esrc [ncells].  Parameters (ode.*, cvode.*)
+        as left by the last react_rk64 / react_cvode call or set through _parm.  Returns react()'s int."""
+        ncells = y.shape[0]
+        h = self.lib.peleref_reactor_create(key.encode(), reactor_type, ncells)
+        try:
+            self.lib.peleref_react_flat.restype = C.c_int
+            self.lib.peleref_react_flat.argtypes = [C.c_void_p, dp, dp, dp, dp, C.c_double, C.c_double, C.c_int]
+            return self.lib.peleref_react_flat(h, _p(y), _p(ysrc), _p(e), _p(esrc), dt, time, ncells)
+        finally:
+            self.lib.peleref_reactor_destroy(h)
+
     def react_rk64(self, st, dt, time=0.0, atol=1e-10, reactor_type=1, nsub=(10, 5, 500)):
         self._parm("ode", "atol", repr(atol))
         self._parm("ode", "rk64_nsubsteps_guess", nsub[0])

@@ -28,6 +28,7 @@ struct prx_handle
   std::mutex host_mutex;        // the *_host calls share one staging buffer: serialised per handle
   SchedParams sched;
   long long last_ncells;
+  int last_layout;
   // staging for the *_host convenience calls
   double* d_stage;
   size_t d_stage_bytes;
@@ -460,8 +461,9 @@ static int react_args(prx_handle* h, const BoxArgs& a, cudaStream_t stream)
   DeviceGuard g(h->device);
   // per-launch step sum (for the value ReactorBase::react returns)
   if (!h->keep_last_steps) {
-    PRX_CUDA(h, cudaMemsetAsync(&h->d_stats->v[ST_LAST_STEPS], 0, sizeof(unsigned long long), stream));
+    PRX_CUDA(h, cudaMemsetAsync(&h->d_stats->v[ST_LAST_STEPS], 0, 2 * sizeof(unsigned long long), stream)); // + ST_LAST_MAXRHS
     h->last_ncells = 0;
+    h->last_layout = a.layout;
   }
   h->last_ncells += a.ncells;
   cudaError_t e;
@@ -881,7 +883,7 @@ int prx_last_react_return(prx_handle* h)
   if (h == nullptr) {
     return PRX_ERR_BAD_ARG;
   }
-  if (h->cfg.reactor_kind == PRX_REACTOR_CVODE) {
+  if (h->cfg.reactor_kind == PRX_REACTOR_CVODE && h->last_layout == LAYOUT_ARRAY4) {
     return 20; // ReactorCvode.cpp:1463-1464: "Dummy, the return value is no longer used"
   }
   DeviceGuard g(h->device);
@@ -889,6 +891,15 @@ int prx_last_react_return(prx_handle* h)
     return 0;
   }
   unsigned long long v = 0;
+  if (h->cfg.reactor_kind == PRX_REACTOR_CVODE) {
+    // 1-D react (ReactorCvode.cpp:1673-1687): nfe + nfeLS of the call.  The reference integrates the ncells cells of one
+    // call as ONE coupled system; here every cell is its own system (see include/pelerx_b200.h), so the work count
+    // reported is the largest per-cell nfe + nfeDQ - identical to the reference's for ncells = 1.
+    if (cudaMemcpy(&v, &h->d_stats->v[ST_LAST_MAXRHS], sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) {
+      return 0;
+    }
+    return (int)v;
+  }
   if (cudaMemcpy(&v, &h->d_stats->v[ST_LAST_STEPS], sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) {
     return 0;
   }

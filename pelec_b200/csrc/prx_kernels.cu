@@ -57,7 +57,7 @@ constexpr unsigned FULL = 0xffffffffu;
 
 struct LaneStats
 {
-  unsigned long long cells, masked, steps, rhs, jac, setups, newton, errfail, convfail, failed, maxsteps;
+  unsigned long long cells, masked, steps, rhs, jac, setups, newton, errfail, convfail, failed, maxsteps, maxrhs;
 };
 
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
@@ -88,6 +88,7 @@ __device__ __forceinline__ void flush_stats(const LaneStats& ls, DevStats* st)
     v[i] = warp_sum(v[i]);
   }
   const unsigned long long mx = warp_max(ls.maxsteps);
+  const unsigned long long mr = warp_max(ls.maxrhs);
   if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < 10; i++) {
@@ -97,6 +98,7 @@ __device__ __forceinline__ void flush_stats(const LaneStats& ls, DevStats* st)
     }
     atomicMax(&st->v[ST_MAXSTEPS], mx);
     atomicAdd(&st->v[ST_LAST_STEPS], v[2]);
+    atomicMax(&st->v[ST_LAST_MAXRHS], mr);
   }
 }
 
@@ -480,6 +482,7 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
       ls.cells++;
       ls.steps += s.nst;
       ls.rhs += s.nfe + s.nfeDQ;
+      ls.maxrhs = (unsigned long long)(s.nfe + s.nfeDQ) > ls.maxrhs ? (unsigned long long)(s.nfe + s.nfeDQ) : ls.maxrhs;
       ls.jac += s.nje;
       ls.setups += s.nsetups;
       ls.newton += s.nni;
@@ -675,6 +678,7 @@ __global__ void __launch_bounds__(32) PRX_CAT(bdf2_kernel_, PRX_MECH_SUFFIX)(
       ls.cells++;
       ls.steps += s.nst;
       ls.rhs += s.nfe + s.nfeDQ;
+      ls.maxrhs = (unsigned long long)(s.nfe + s.nfeDQ) > ls.maxrhs ? (unsigned long long)(s.nfe + s.nfeDQ) : ls.maxrhs;
       ls.jac += s.nje;
       ls.setups += s.nsetups;
       ls.newton += s.nni;
@@ -927,6 +931,7 @@ __global__ void __launch_bounds__(128, PRX_BDF3_MINBLOCKS / 4) PRX_CAT(bdf3_kern
       ls.cells++;
       ls.steps += s.nst;
       ls.rhs += s.nfe + s.nfeDQ;
+      ls.maxrhs = (unsigned long long)(s.nfe + s.nfeDQ) > ls.maxrhs ? (unsigned long long)(s.nfe + s.nfeDQ) : ls.maxrhs;
       ls.jac += s.nje;
       ls.setups += s.nsetups;
       ls.newton += s.nni;
@@ -985,6 +990,213 @@ cudaError_t launch_bdf3(const BoxArgs& a, const BdfParams& p, const SchedParams&
   return e != cudaSuccess ? e : e2;
 }
 #endif // PRX_HAVE_BDF2
+
+// =====================================================================================
+// BDF kernel, fourth generation ("fat threads"): the WHOLE integrator state on chip at one cell per thread
+// =====================================================================================
+// ncu on the first-generation kernel (profiles/r01n_*): 4.7 KB of thread-local state per cell x 21 warps
+// per SM = 466 MB of local memory against a 126 MB L2 -> 112 KB of DRAM traffic per cell (417x the algorithmic bytes),
+// 41 % of the stall samples on local-memory loads.  On-chip capacity (227 KB of shared memory per SM) holds the state
+// of ~130 LiDryer cells, so this kernel runs ONE block of NT = 128 threads per SM with
+//  * every integrator vector, the Newton matrix and the external species source in shared-memory columns
+//    (element i at base[i*NT + tid]: conflict-free, compile-time offsets),
+//  * the straight-line generated RHS / Jacobian in registers (up to 255 per thread: the instruction-level parallelism of
+//    the 21 independent reactions replaces the thread-level parallelism the state does not leave room for),
+//  * savedJ (written once, read once per linear setup) thread-local,
+//  * the same phase barrier / sorted work queue / inline Jacobian + LU service as the first generation.
+struct SrcScal
+{
+  double rhoe_init, rhoesrc;
+};
+
+#define PRX_HAVE_BDF4 (PRX_NUM_SPECIES <= 12)
+#if PRX_HAVE_BDF4
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) PRX_CAT(bdf4_kernel_, PRX_MECH_SUFFIX)(
+  const BoxArgs a, const BdfParams p, const SchedParams sp, int* __restrict__ queue, DevStats* __restrict__ stats)
+{
+  typedef BdfCellT<BdfStoreSmem<NT, true>, SrcScal> Cell;
+  Cell s;
+  s.base = prx_dyn_smem + threadIdx.x;
+  s.nz = p.qmax + 1;
+  int cell = -1;
+  bool exhausted = false;
+  int req = REQ_NONE;
+  LaneStats ls = {};
+  BdfParams pc = p;
+  pc.array4_semantics = 0; // the initial T solve is done in the refill below
+  for (;;) {
+    // ---- (1) refill ----
+    int got = fetch_cell((cell < 0) && !exhausted, queue, a.ncells);
+    if (got >= 0 && a.order != nullptr) {
+      got = a.order[got];
+    }
+    if (got == -2) {
+      exhausted = true;
+    } else if (got >= 0) {
+      double y0[NEQ];
+      CellSrc cs;
+      if (load_cell(a, got, y0, cs, p.clean_init_massfrac)) {
+        cell = got;
+        s.src.rhoe_init = cs.rhoe_init;
+        s.src.rhoesrc = cs.rhoesrc;
+        double rho = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+          s.zn(0)[k] = y0[k];
+          s.scratch()[k] = cs.rYsrc[k];
+          rho += y0[k];
+        }
+        double temp = y0[N];
+        if (p.array4_semantics) { // box_flatten re-solves T from (e, Y) (ReactorUtils.H:206-219)
+          const double rho_inv = 1.0 / rho;
+          double Y[N];
+#pragma unroll
+          for (int k = 0; k < N; k++) {
+            Y[k] = y0[k] * rho_inv;
+          }
+          t_from_energy(p.reactor_type, cs.rhoe_init * rho_inv, Y, temp);
+        }
+        s.zn(0)[N] = temp;
+        bdf_begin(s, pc, a.dt, a.time);
+        req = REQ_NONE;
+      } else {
+        store_masked(a, got);
+        ls.masked++;
+      }
+    }
+    if (!__syncthreads_or(!(exhausted && (cell < 0)))) {
+      break;
+    }
+    // ---- (2) control, Jacobian / LU requests served inside (every iteration ends in one RHS per warp) ----
+    for (;;) {
+      if (cell >= 0 && req == REQ_NONE) {
+        req = bdf_resume(s, pc);
+      }
+      if (__ballot_sync(FULL, req == REQ_JAC || req == REQ_LU) == 0u) {
+        break;
+      }
+      if (req == REQ_JAC) {
+        double yy[NEQ];
+#pragma unroll
+        for (int k = 0; k < NEQ; k++) {
+          yy[k] = s.y()[k];
+        }
+        double* J = s.savedJ();
+        jac_analytic(p.reactor_type, yy, J, [J](const int row, const int col, const double v) { J[col * NEQ + row] = v; });
+        req = REQ_NONE;
+      }
+      if (req == REQ_LU) {
+        s.lu_info = dense_getrf_small(s.A(), s.piv(), s.perm());
+        req = REQ_NONE;
+      }
+    }
+    __syncthreads(); // phase barrier: the block's warps walk through the RHS code together (instruction cache)
+    // ---- (3) serve ----
+    if (req == REQ_RHS) {
+      double yy[NEQ], yd[NEQ];
+      CellSrc cs;
+      cs.rhoe_init = s.src.rhoe_init;
+      cs.rhoesrc = s.src.rhoesrc;
+      typename Cell::Vec vin = s.vec(s.in_sel);
+#pragma unroll
+      for (int k = 0; k < NEQ; k++) {
+        yy[k] = vin[k];
+      }
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        cs.rYsrc[k] = s.scratch()[k];
+      }
+      rhs(s.t_eval, p.reactor_type, yy, yd, cs);
+      typename Cell::Vec vout = s.vec(s.out_sel);
+#pragma unroll
+      for (int k = 0; k < NEQ; k++) {
+        vout[k] = yd[k];
+      }
+      req = REQ_NONE;
+    }
+    if (req == REQ_DONE) {
+      double yy[NEQ];
+      CellSrc cs;
+      cs.rhoe_init = s.src.rhoe_init;
+      cs.rhoesrc = s.src.rhoesrc;
+#pragma unroll
+      for (int k = 0; k < NEQ; k++) {
+        yy[k] = s.y()[k];
+      }
+      store_cell(a, cell, yy, cs, p.reactor_type, double(s.nfe + s.nfeDQ), p.clean_init_massfrac, p.array4_semantics != 0);
+      ls.cells++;
+      ls.steps += s.nst;
+      ls.rhs += s.nfe + s.nfeDQ;
+      ls.maxrhs = (unsigned long long)(s.nfe + s.nfeDQ) > ls.maxrhs ? (unsigned long long)(s.nfe + s.nfeDQ) : ls.maxrhs;
+      ls.jac += s.nje;
+      ls.setups += s.nsetups;
+      ls.newton += s.nni;
+      ls.errfail += s.netf;
+      ls.convfail += s.ncfn;
+      ls.failed += (s.flag != CV_SUCCESS);
+      ls.maxsteps = (unsigned long long)s.nst > ls.maxsteps ? s.nst : ls.maxsteps;
+      cell = -1;
+      req = REQ_NONE;
+    }
+  }
+  flush_stats(ls, stats);
+}
+
+template <int NT>
+cudaError_t launch_bdf4_nt(const BoxArgs& a, const BdfParams& p, const SchedParams& sp, int* queue, DevStats* stats, cudaStream_t stream)
+{
+  typedef BdfStoreSmem<NT, true> Store;
+  auto kern = PRX_CAT(bdf4_kernel_, PRX_MECH_SUFFIX)<NT>;
+  const size_t smem = sizeof(double) * NT * (size_t)Store::doubles_per_thread(p.qmax);
+  int dev = 0, sms = 148, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    return e;
+  }
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem) != cudaSuccess || per_sm < 1) {
+    return cudaErrorInvalidConfiguration;
+  }
+  long long grid = (long long)sms * per_sm;
+  const long long needed = ((long long)a.ncells + NT - 1) / NT;
+  grid = needed < grid ? needed : grid;
+  e = cudaMemsetAsync(queue, 0, sizeof(int), stream);
+  if (e != cudaSuccess) {
+    return e;
+  }
+  kern<<<(int)grid, NT, smem, stream>>>(a, p, sp, queue, stats);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bdf4(const BoxArgs& a, const BdfParams& p, const SchedParams& sp, int* queue, DevStats* stats, cudaStream_t stream)
+{
+  // the largest block whose state fits the SM's shared memory (one block per SM)
+  int dev = 0, max_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const size_t per_thread = sizeof(double) * (size_t)BdfStoreSmem<32, true>::doubles_per_thread(p.qmax);
+  int nt = (int)((size_t)max_optin / per_thread) / 32 * 32;
+  if (sp.block_warps > 0 && sp.block_warps * 32 < nt) {
+    nt = sp.block_warps * 32;
+  }
+  if (nt >= 128) {
+    return launch_bdf4_nt<128>(a, p, sp, queue, stats, stream);
+  }
+  if (nt >= 96) {
+    return launch_bdf4_nt<96>(a, p, sp, queue, stats, stream);
+  }
+  if (nt >= 64) {
+    return launch_bdf4_nt<64>(a, p, sp, queue, stats, stream);
+  }
+  if (nt >= 32) {
+    return launch_bdf4_nt<32>(a, p, sp, queue, stats, stream);
+  }
+  return cudaErrorInvalidConfiguration;
+}
+#endif // PRX_HAVE_BDF4
 
 // =====================================================================================
 // BDF kernel, third generation: G lanes per cell (prx_coop.cuh)
@@ -1217,6 +1429,7 @@ __global__ void __launch_bounds__(32, PRX_COOP_MINBLOCKS) PRX_CAT(bdfc_kernel_, 
         ls.cells++;
         ls.steps += s.nst;
         ls.rhs += s.nfe + s.nfeDQ;
+        ls.maxrhs = (unsigned long long)(s.nfe + s.nfeDQ) > ls.maxrhs ? (unsigned long long)(s.nfe + s.nfeDQ) : ls.maxrhs;
         ls.jac += s.nje;
         ls.setups += s.nsetups;
         ls.newton += s.nni;
@@ -1500,6 +1713,11 @@ cudaError_t launch_bdf(
     return launch_bdf3<true>(a, p, sp, queue, stats, stream);
   }
 #endif
+#if PRX_HAVE_BDF4
+  if (variant == 5) {
+    return launch_bdf4(a, p, sp, queue, stats, stream);
+  }
+#endif
 #if PRX_HAVE_BDF1
   auto kern = PRX_CAT(bdf_kernel_, PRX_MECH_SUFFIX);
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1); // state lives in L1-cached local memory
@@ -1537,6 +1755,13 @@ int effective_bdf_variant(const SchedParams& sp)
     v = 0;
   }
 #endif
+#if !PRX_HAVE_BDF4
+  if (v == 5) {
+    v = 0;
+  }
+#else
+  (void)0;
+#endif
 #if !PRX_HAVE_BDF1
   if (v == 0) {
     v = 32;
@@ -1561,6 +1786,8 @@ const char* kernel_name(int reactor_kind, const SchedParams& sp)
   case 3:
   case 4:
     return "bdf3_kernel_" PRX_STR(PRX_MECH_SUFFIX);
+  case 5:
+    return "bdf4_kernel_" PRX_STR(PRX_MECH_SUFFIX);
   default:
     return "bdf_kernel_" PRX_STR(PRX_MECH_SUFFIX);
   }

@@ -45,11 +45,12 @@ struct BoxArgs
 // device-side counters (unsigned long long so that atomicAdd applies)
 struct DevStats
 {
-  unsigned long long v[12];
+  unsigned long long v[14];
 };
 enum StatIdx {
   ST_CELLS = 0, ST_MASKED, ST_STEPS, ST_RHS, ST_JAC, ST_SETUPS, ST_NEWTON, ST_ERRFAIL, ST_CONVFAIL,
-  ST_FAILED, ST_MAXSTEPS, ST_LAST_STEPS
+  ST_FAILED, ST_MAXSTEPS, ST_LAST_STEPS,
+  ST_LAST_MAXRHS // largest nfe + nfeDQ of a cell of the last react call (what the 1-D CVODE react returns)
 };
 
 // scheduling knobs of the warp loop (see prx_kernels.cu)

@@ -769,6 +769,63 @@ def emit(mech, flavour):
     return Emitter(load(mech), flavour).emit()
 
 
+# ---------------------------------------------------------------------------------------------
+# Literal pool of the straight-line device code
+# ---------------------------------------------------------------------------------------------
+# ncu on the round-1 kernels (profiles/r02a_prof_rk64_lidryer_64_opcodes.txt): 50 % of the executed instructions of the
+# straight-line chemistry were UMOV / MOV / IMAD.MOV pairs materialising 64-bit literals (sm_100a FP64 instructions take
+# a register, a uniform register or a 32-bit immediate = the HIGH word of a double, never a full 64-bit immediate), and the
+# RK64 kernel was issue-bound at 60 % with the FP64 pipe 40 % busy.  constify() moves every literal whose low word is not
+# zero into one __constant__ table, in order of first use: neighbouring literals of an expression become neighbouring table
+# entries, which ptxas fetches with ONE LDCU.128 per pair (uniform registers) instead of four UMOVs.
+_LIT_RE = None
+
+
+def _cheap_literal(tok):
+    import struct
+    return (struct.unpack("<Q", struct.pack("<d", float(tok)))[0] & 0xffffffff) == 0
+
+
+def constify(text, max_entries=6000):
+    """Rewrite the straight-line functions of a cuda-flavour header so that expensive literals come from prx_k[]."""
+    import re
+    global _LIT_RE
+    if _LIT_RE is None:
+        _LIT_RE = re.compile(r"(?<![\w.\]\)])(\d+\.\d*(?:[eE][-+]?\d+)?|\d+[eE][-+]?\d+)(?![\w.])")
+    begin = text.index("PRX_DEVFN void cv_R(")
+    end = text.index("#ifdef PRX_MATH_REDIRECT\n#undef exp")
+    head, body, tail = text[:begin], text[begin:end], text[end:]
+    pool, order = {}, []
+
+    def sub(m):
+        tok = m.group(1)
+        if _cheap_literal(tok):
+            return tok
+        if tok not in pool:
+            if len(order) >= max_entries:
+                return tok
+            pool[tok] = len(order)
+            order.append(tok)
+        return "PRX_K(%d)" % pool[tok]
+
+    body = body.replace("PRX_LN10", "2.30258509299404568402")
+    # quotients of two literals were folded by the compiler (IEEE division, same bits as Python's): keep them folded
+    num = r"(\d+\.\d*(?:[eE][-+]?\d+)?)"
+    body = re.sub(r"= %s / %s (?=[*/])" % (num, num), lambda m: "= %r " % (float(m.group(1)) / float(m.group(2))), body)
+    body = _LIT_RE.sub(sub, body)
+    if len(order) % 2:
+        order.append("0.0")
+    tab = ["// literal pool of the straight-line code (see gen.py constify)",
+           "#ifdef PRX_HOST_TEST",
+           "static const double prx_k[%d] = {%s};" % (len(order), ", ".join(order)),
+           "#else",
+           "static __constant__ __align__(16) double prx_k[%d] = {%s};" % (len(order), ", ".join(order)),
+           "#endif",
+           "#define PRX_K(i) prx_k[i]",
+           ""]
+    return head + "\n".join(tab) + "\n" + body + tail
+
+
 def write_if_changed(path, text):
     os.makedirs(os.path.dirname(path), exist_ok=True)
     if os.path.exists(path) and open(path).read() == text:
@@ -785,7 +842,11 @@ def generate_all(repo_root, mechs=("LiDryer", "drm19", "dodecane_lu")):
         write_if_changed(p, emit(m, "c"))
         out.append(p)
         p = os.path.join(repo_root, "pelec_b200", "csrc", "gen", "mech_%s.cuh" % m)
-        write_if_changed(p, emit(m, "cuda"))
+        text = emit(m, "cuda")
+        # dodecane_lu's mechanism tables already fill the 64 KB constant bank: its straight-line code keeps inline literals
+        if os.environ.get("PRX_GEN_CONSTIFY", "1") != "0" and len(load(m)["species"]) <= 32:
+            text = constify(text)
+        write_if_changed(p, text)
         out.append(p)
     return out
 

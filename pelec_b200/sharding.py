@@ -21,20 +21,29 @@ MAX_KEYS = ("max_steps", "device_ms")
 
 
 def chop_domain(ncell: Sequence[int], max_grid_size: int) -> List[BoxT]:
-    """BoxArray(domain).maxSize(max_grid_size): every direction is cut into ceil(n/mgs) nearly equal
-    pieces (AMReX_BoxArray.cpp maxSize -> Box::chop semantics: piece lengths differ by at most one and
-    the longer pieces come first).  Boxes are returned in AMReX's order (x fastest)."""
+    """BoxArray(domain).maxSize(max_grid_size) = BoxList::maxSize (amrex/Src/Base/AMReX_BoxList.cpp:765-820), per
+    direction: while the chunk and the length are both even, halve both (the pieces stay aligned to that power of two);
+    cut the reduced length nlen into numblk = ceil(nlen/bs) pieces of nlen // numblk cells, the first nlen % numblk one cell
+    longer; scale back.  Length 10 / chunk 4 -> 4, 4, 2; length 100 / chunk 32 -> 28, 24, 24, 24.  Boxes are returned in
+    AMReX's order (x fastest)."""
     cuts = []
     for n in ncell:
         if n <= 0 or max_grid_size <= 0:
             raise ValueError("chop_domain: sizes must be positive")
-        nb = -(-n // max_grid_size)
-        base, extra = divmod(n, nb)
-        edges, lo = [], 0
-        for b in range(nb):
-            ln = base + (1 if b < extra else 0)
-            edges.append((lo, lo + ln - 1))
-            lo += ln
+        if n <= max_grid_size:
+            cuts.append([(0, n - 1)])
+            continue
+        ratio, bs, nlen = 1, max_grid_size, n
+        while bs % 2 == 0 and nlen % 2 == 0:
+            ratio, bs, nlen = ratio * 2, bs // 2, nlen // 2
+        numblk = (nlen + bs - 1) // bs
+        sz = nlen // numblk
+        extra = nlen - sz * numblk
+        edges = []
+        for b in range(numblk):
+            lo = b * (sz + 1) * ratio if b < extra else (b * sz + extra) * ratio
+            hi = lo + ((sz + 1) if b < extra else sz) * ratio - 1
+            edges.append((lo, hi))
         cuts.append(edges)
     return [((x[0], y[0], z[0]), (x[1], y[1], z[1])) for z in cuts[2] for y in cuts[1] for x in cuts[0]]
 

@@ -15,7 +15,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from oracle.pyoracle import Oracle  # noqa: E402
 
-TABLES = {"LiDryer": "LiDryer_H2_p1_phi0_4000tu0300.dat", "drm19": "PMF_CH4_1bar_300K_DRM_MixAvg.dat"}
+TABLES = {"LiDryer": "LiDryer_H2_p1_phi0_4000tu0300.dat", "drm19": "PMF_CH4_1bar_300K_DRM_MixAvg.dat",
+          "dodecane_lu": "PMF_NC12H26_1bar_300K_DodecaneLu.dat"}
+NSTATES_OF = {"dodecane_lu": 512}
 NSTATES = 2048
 
 
@@ -29,7 +31,11 @@ def lcg_uniform(n, seed=12345):
 
 
 def main():
+    only = sys.argv[1:]
     for mech, fname in TABLES.items():
+        if only and mech not in only:
+            continue
+        NSTATES = NSTATES_OF.get(mech, 2048)
         path = os.path.join("/root/reference/Exec/RegTests/PMF", fname)
         lines = open(path).read().splitlines()
         names = [t.strip('"') for t in lines[0].split("=")[1].split()]
@@ -41,7 +47,8 @@ def main():
         T = np.interp(xs, x, data[:, names.index("temp")])
         X = np.zeros((NSTATES, orc.N))
         for k, sp in enumerate(orc.species):
-            X[:, k] = np.interp(xs, x, data[:, names.index(sp)])
+            col = sp if sp in names else sp.replace("*", "S")  # the table spells CH2* as CH2S
+            X[:, k] = np.interp(xs, x, data[:, names.index(col)])
         X = np.maximum(X, 0.0)
         X /= X.sum(axis=1, keepdims=True)
         Y = orc.x2y(X)

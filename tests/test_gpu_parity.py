@@ -299,7 +299,7 @@ def test_flatten_unflatten_match_reference_semantics(ordering):
     r.close()
 
 
-BDF_VARIANTS = {"LiDryer": (0, 1, 2, 3, 4, 8, 16, 32), "drm19": (0, 2, 3, 8, 16, 32), "dodecane_lu": (32,)}
+BDF_VARIANTS = {"LiDryer": (0, 1, 2, 3, 4, 5, 8, 16, 32), "drm19": (0, 2, 3, 8, 16, 32), "dodecane_lu": (32,)}
 
 
 @pytest.mark.parametrize("variant", sorted({v for vs in BDF_VARIANTS.values() for v in vs}))
@@ -315,7 +315,7 @@ def test_every_bdf_kernel_generation_matches_golden(mech, variant, monkeypatch):
     kw = CVODE_SETTINGS[0]
     r = make_reactor("ReactorCvode", mech, **cvode_parm(kw))
     name = r.kernel_name()
-    assert name.startswith({0: "bdf_kernel_", 1: "bdf2_", 2: "bdf2_", 3: "bdf3_", 4: "bdf3_"}.get(variant, "bdfc_kernel_")[:4])
+    assert name.startswith({0: "bdf_kernel_", 1: "bdf2_", 2: "bdf2_", 3: "bdf3_", 4: "bdf3_", 5: "bdf4_"}.get(variant, "bdfc_kernel_")[:4])
     s = golden_state(g)
     s.mask[::7] = -1
     react_host(r, s, float(g["dt"]))

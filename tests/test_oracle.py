@@ -167,3 +167,33 @@ def test_oracle_vs_reference_enthalpy_form(mech, orc):
         ref.react_rk64(b, 1e-6, atol=1e-10, reactor_type=2)
         orc.react_rk64(a, 1e-6, atol=1e-10, reactor_type=2)
         assert np.array_equal(a.rY, b.rY) and np.array_equal(a.T, b.T) and np.array_equal(a.FC, b.FC)
+
+
+def test_ignition_trajectory_oracle_vs_reference_fixture_and_cantera():
+    """PeleC's zero-D known answer (PC/Exec/RegTests/zeroD: H2/O2/N2 at 1000 K, 1 atm, LiDryer; cantera_soln): the C
+    restatement driven through 1000 successive react calls of 1e-6 s stays on the reference's own trajectory
+    (tests/golden/ignition_LiDryer.npz, made by tests/golden/make_golden2.py) and on the Cantera curve away from the
+    front.  This pins the multi-call time-advance path (ReactEval main.cpp:484-526) of the oracle."""
+    import os
+    from oracle.pyoracle import BoxState
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ignition_LiDryer.npz"))
+    orc = Oracle("LiDryer")
+    st = BoxState(g["rY0"], g["T0"], g["rE0"])
+    ncall, dt = int(g["ncall"]), float(g["dt"])
+    T, rY = np.zeros(ncall), np.zeros((ncall, orc.N))
+    for n in range(ncall):
+        orc.react_cvode(st, dt, time=n * dt, rtol=1e-10, atol=1e-10, max_order=4, solve_type="denseAJ_direct")
+        T[n], rY[n] = st.T[0], st.rY[:, 0]
+    rho = g["rY0"].sum()
+    dT = np.abs(T - g["cvode_T"]) / g["cvode_T"]
+    dY = np.abs(rY - g["cvode_rY"]).max(axis=1) / rho
+    front = (np.arange(ncall) >= 125) & (np.arange(ncall) < 150)
+    assert dT[~front].max() < 1e-9 and dY[~front].max() < 1e-9
+    assert dT[front].max() < 1e-7 and dY[front].max() < 1e-7
+    k = np.arange(9, ncall, 10)
+    ct, cT = g["cantera_t"], g["cantera_T"]
+    away = (ct < 1.15e-4) | (ct > 1.45e-4)
+    assert (np.abs(T[k] - cT) / cT)[away].max() < 5e-4
+    assert abs(T[-1] - cT[-1]) / cT[-1] < 1e-5
+    # the reference's RK64 never rejects a step and returns NaN at the front: the fixture records that
+    assert np.isfinite(g["rk64_T"][:130]).all() and not np.isfinite(g["rk64_T"][140])

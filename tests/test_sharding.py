@@ -17,8 +17,11 @@ def test_chop_and_knapsack():
     boxes = sharding.chop_domain((256, 256, 256), 64)
     assert len(boxes) == 64 and sum(map(sharding.box_cells, boxes)) == 256 ** 3
     assert boxes[0] == ((0, 0, 0), (63, 63, 63)) and boxes[1][0] == (64, 0, 0)  # x fastest
-    ragged = sharding.chop_domain((10, 7, 1), 4)  # 10 -> 4,3,3 ; 7 -> 4,3
-    assert [b[1][0] - b[0][0] + 1 for b in ragged[:3]] == [4, 3, 3]
+    # BoxList::maxSize halves chunk and length while both are even (AMReX_BoxList.cpp:773-785): 10 / 4 -> 4, 4, 2 ; 7 / 4 -> 4, 3
+    ragged = sharding.chop_domain((10, 7, 1), 4)
+    assert [b[1][0] - b[0][0] + 1 for b in ragged[:3]] == [4, 4, 2]
+    assert [b[1][0] - b[0][0] + 1 for b in sharding.chop_domain((100, 1, 1), 32)] == [28, 24, 24, 24]
+    assert [b[1][0] - b[0][0] + 1 for b in sharding.chop_domain((96, 1, 1), 64)] == [64, 32]
     seen = np.zeros((10, 7, 1), dtype=int)
     for lo, hi in ragged:
         seen[lo[0]:hi[0] + 1, lo[1]:hi[1] + 1, lo[2]:hi[2] + 1] += 1

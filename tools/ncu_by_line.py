@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Stall samples of one kernel attributed to CUDA source lines: joins the SASS rows of an .ncu-rep (source page) with
 the line table of the cubin the kernel came from (nvdisasm -g; needs -lineinfo and the SAME build).
-usage: tools/ncu_by_line.py rep.ncu-rep file.o kernel-substring [top]"""
+usage: tools/ncu_by_line.py rep.ncu-rep|source.csv[.gz] file.o kernel-substring [top]
+(the first function of the cubin whose mangled name contains the substring is taken)"""
 import collections, csv, io, os, re, subprocess, sys, tempfile
 rep, obj, kern = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
@@ -9,11 +10,13 @@ tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, capture_output=True)
 cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
 out = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
-infn, cur, lines = False, None, []
+infn, cur, lines, taken = False, None, [], None
 for line in out.splitlines():
     m = re.match(r"\s*\.text\.(\S+):", line)
     if m:
-        infn = kern in m.group(1)
+        infn = kern in m.group(1) and taken in (None, m.group(1))
+        if infn:
+            taken = m.group(1)
         continue
     if not infn:
         continue
@@ -23,7 +26,13 @@ for line in out.splitlines():
         continue
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
         lines.append(cur)
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+if rep.endswith(".gz"):
+    import gzip
+    src = gzip.open(rep, "rt").read()
+elif rep.endswith(".csv"):
+    src = open(rep).read()
+else:
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
