@@ -49,6 +49,11 @@ def parse():
                          "(tests/golden/pmf_states_<mech>.npz, SURVEY 8(d) set B: the divergent workload)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", default="auto",
+                    help="sharded-domain (strong scaling) blocks added to the JSON line: 'auto' = BASELINE configs[2] "
+                         "(256^3 drm19, max_grid_size 64) at every N and configs[3] (128^3 dodecane_lu, max_grid_size 32) at "
+                         "N >= 8; 'none'; or a comma list of mech:n:max_grid_size")
+    ap.add_argument("--strong-steps", type=int, default=2)
     return ap.parse_args()
 
 
@@ -283,6 +288,21 @@ def run_b200(a):
     value = cells_all / (total_ms * 1e-3)
     e2e_value = ncell * e2e_steps * world / t_e2e
 
+    strong = []
+    if a.strong != "none" and a.reactor == "ReactorCvode" and a.states == "reacteval":
+        specs = []
+        if a.strong == "auto":
+            if a.mech == "LiDryer" and a.n == 128:  # the default (driver) invocation only
+                specs.append(("drm19", 256, 64))
+                if world >= 8:
+                    specs.append(("dodecane_lu", 128, 32))
+        else:
+            for item in a.strong.split(","):
+                m, nn, g = item.split(":")
+                specs.append((m, int(nn), int(g)))
+        for spec in specs:
+            strong.append(strong_block(a, spec, dev, local, world, rank))
+
     if rank == 0:
         oc = gen.op_counts(a.mech)
         c = dict(zip(("cells", "n_steps", "n_rhs", "n_jac", "n_setups", "n_newton", "n_errfail", "n_convfail",
@@ -322,6 +342,7 @@ def run_b200(a):
                 "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
                 "frac": achieved / peak.value if peak.value > 0 else None,
                 "traffic": ncu_traffic(r.kernel_name(), ncell),
+                "sass": sass_flops(r.kernel_name(), ncell, kms, peak.value),
                 "peak_source": "measured in this run: register-resident DFMA chains (prx_measure_fp64_peak)",
                 "kernel": r.kernel_name(),
                 "kernel_ms": kms, "flops_per_launch": flops_per_launch,
@@ -333,6 +354,8 @@ def run_b200(a):
             "failed_cells": c["n_failed"],
             "clocks": sampler.summary(),
         }
+        if strong:
+            line["strong"] = strong
         if not a.no_cpu_baseline:
             cb = cpu_throughput(a, a.cpu_seconds)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -340,6 +363,130 @@ def run_b200(a):
     r.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def profile_states(mech, n):
+    """The n distinct ReactEval states of an n^3 box (they depend on j only): rY_j [N, n], T_j [n], rE_j [n]."""
+    # same formulas as synth_states, one cell per j
+    import numpy as np
+    from pelec_b200.mechgen import gen
+    d = gen.load(mech)
+    names = d["species"]
+    N = len(names)
+    mw = np.array([float(x) for x in d["mw"]])
+    imw = np.array([float(x) for x in d["imw"]])
+    Ru = float(d["Ru"])
+    fuel = {"LiDryer": "H2", "drm19": "CH4", "dodecane_lu": "NC12H26"}[mech]
+    X = np.zeros(N)
+    X[names.index("O2")], X[names.index(fuel)], X[names.index("N2")] = 0.2, 0.1, 0.7
+    Y = X * mw / (X * mw).sum()
+    y = -1.0 + (np.arange(n) + 0.5) * (2.0 / n)
+    Tj = 2000.0 + 500.0 * y / 2.0 + 100.0 * np.sin(2.0 * 3.1415926535897932 * y / 0.5)
+    rho = 1013250.0 / (Ru * Tj * (Y * imw).sum())
+    th = d["thermo"]["speciesInternalEnergy"]
+    basis = {"1": lambda T: np.ones_like(T), "T": lambda T: T, "T2": lambda T: T * T, "T3": lambda T: T ** 3,
+             "T4": lambda T: T ** 4, "invT": lambda T: 1.0 / T}
+    e = np.zeros(n)
+    for k in range(N):
+        if Y[k] == 0.0:
+            continue
+        tm = th[k]["tmid"]
+        lo = sum(float(c) * basis[b](Tj) for c, b in th[k]["lo"])
+        hi = sum(float(c) * basis[b](Tj) for c, b in th[k]["hi"])
+        e += Y[k] * np.where(Tj < (tm if tm is not None else 1e99), lo, hi) * Ru * Tj * imw[k]
+    return Y[:, None] * rho[None, :], Tj, rho * e
+
+
+def strong_block(a, spec, dev, local, world, rank):
+    """Sharded-domain run (BASELINE configs[2]/[3]): ONE n^3 domain cut into boxes exactly as the reference does
+    (BoxArray::maxSize, PP/Testing/Exec/ReactEval/main.cpp:198-203 -> sharding.chop_domain), boxes owned by ranks through the
+    cost-weighted knapsack AMReX uses (DistributionMapping KNAPSACK -> sharding.knapsack) - cell counts for the first call,
+    the previous call's per-box sum of FC afterwards (PeleC's Work_Estimate, PC/Source/React.cpp:316-322) - every rank reacts
+    only its own boxes, no data-path collective.  Time = max over ranks of the CUDA-event time of a pass over the rank's boxes."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pelec_b200 import sharding
+    from pelec_b200.reactor import Array4, Box, ReactorB200
+    mech, n, mgs = spec
+    boxes = sharding.chop_domain((n, n, n), mgs)
+    rYj, Tj, rEj = profile_states(mech, n)
+    N = rYj.shape[0]
+    d_rYj, d_Tj, d_rEj = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (rYj, Tj, rEj))
+    parm = {"ode__atol": a.atol, "ode__rtol": a.rtol, "cvode__max_order": a.max_order, "cvode__solve_type": "denseAJ_direct"}
+    r = ReactorB200.create("ReactorCvode", mech, **parm)
+    r.init(1, 1, device=local)
+    stream = torch.cuda.current_stream(dev)
+
+    def build(ib):
+        (x0, y0, z0), (x1, y1, z1) = boxes[ib]
+        bx, by, bz = x1 - x0 + 1, y1 - y0 + 1, z1 - z0 + 1
+        ex = lambda v, nc: v.reshape(nc, 1, by, 1).expand(nc, bz, by, bx).contiguous()
+        return {"shape": (bx, by, bz), "rY0": ex(d_rYj[:, y0:y1 + 1], N), "T0": ex(d_Tj[y0:y1 + 1], 1), "rE0": ex(d_rEj[y0:y1 + 1], 1)}
+
+    def one_pass(mine, st):
+        """react every owned box once, from pristine copies; returns (device ms, per-box sum of FC)"""
+        work = []
+        for ib in mine:
+            b = st[ib]
+            bx, by, bz = b["shape"]
+            work.append((ib, b["rY0"].clone(), b["T0"].clone(), b["rE0"].clone(),
+                         torch.zeros((N, bz, by, bx), dtype=torch.float64, device=dev),
+                         torch.zeros((1, bz, by, bx), dtype=torch.float64, device=dev),
+                         torch.zeros((1, bz, by, bx), dtype=torch.float64, device=dev),
+                         torch.ones((1, bz, by, bx), dtype=torch.int32, device=dev)))
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for ib, rY, T, rE, rYs, rEs, FC, mask in work:
+            bx, by, bz = st[ib]["shape"]
+            r.react(Box((0, 0, 0), (bx - 1, by - 1, bz - 1)), Array4(rY), Array4(rYs), Array4(T), Array4(rE), Array4(rEs),
+                    Array4(FC), Array4(mask), a.dt, 0.0, stream=stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1), {w[0]: float(w[6].sum()) for w in work}
+
+    def gather_fc(fc):
+        v = torch.zeros(len(boxes), dtype=torch.float64, device=dev)
+        for ib, x in fc.items():
+            v[ib] = x
+        if world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.SUM)  # tiny, off the data path: the cost vector every rank partitions with
+        return v.cpu().tolist()
+
+    owner = sharding.knapsack([sharding.box_cells(b) for b in boxes], world)
+    mine = [i for i, o in enumerate(owner) if o == rank]
+    st = {ib: build(ib) for ib in mine}
+    _, fc = one_pass(mine, st)  # warm-up, cell-count weights; its FC is the cost estimate of the timed passes
+    weights = gather_fc(fc)
+    owner = sharding.knapsack(weights, world)
+    mine = [i for i, o in enumerate(owner) if o == rank]
+    st = {ib: (st[ib] if ib in st else build(ib)) for ib in mine}
+    ms, fcs = [], None
+    for _ in range(max(1, a.strong_steps)):
+        t, fcs = one_pass(mine, st)
+        ms.append(t)
+    my_ms = sum(ms) / len(ms)
+    my_cost = sum(weights[i] for i in mine)
+    t = torch.tensor([my_ms, my_cost], dtype=torch.float64, device=dev)
+    tmax, tsum = t.clone(), t.clone()
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    stats = r.stats()
+    r.close()
+    ncell = n ** 3
+    return {
+        "workload": "%d^3 synthetic %s states (ReactEval initialize_data), ReactorCvode rtol=%g atol=%g max_order=%d, dt=%g s, "
+                    "max_grid_size %d -> %d boxes sharded over %d GPU(s)" % (n, mech, a.rtol, a.atol, a.max_order, a.dt, mgs, len(boxes), world),
+        "mechanism": mech, "cells": ncell, "boxes": len(boxes), "max_grid_size": mgs, "n_gpus": world, "scaling": "strong",
+        "steps": len(ms), "ms_per_step": float(tmax[0]), "value": ncell / (float(tmax[0]) * 1e-3), "unit": UNIT,
+        "partition": "knapsack (LPT) on the previous call's per-box sum of FC",
+        "imbalance_cost": float(tmax[1]) / (float(tsum[1]) / world), "imbalance_ms": float(tmax[0]) / (float(tsum[0]) / world),
+        "boxes_this_rank": len(mine), "failed_cells": stats["n_failed"],
+    }
 
 
 def pmf_states(mech, n):
@@ -360,6 +507,20 @@ def ncu_traffic(kernel, ncell):
         t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]
         return {"dram_bytes": t["dram_bytes_per_cell"] * ncell, "dram_bytes_per_cell": t["dram_bytes_per_cell"],
                 "source": t["source"]}
+    except Exception:
+        return None
+
+
+def sass_flops(kernel, ncell, kernel_ms, peak_tflops):
+    """FP64 operations the kernel really executes (2*DFMA + DMUL + DADD, thread level, from the committed ncu capture of this
+    kernel, profiles/r02_sass_flops.json, scaled per cell) next to the algorithmic model: transcendentals and divisions
+    expand into ~25 FP64 instructions each, so the SASS figure is ~1.8x the algorithmic one (SURVEY.md 8d validation)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_sass_flops.json")))[kernel]
+        f = t["sass_flops_per_cell"] * ncell
+        return {"flops_per_launch": f, "over_algorithmic": t.get("sass_over_model"),
+                "frac_of_peak": f / (kernel_ms * 1e-3) / 1e12 / peak_tflops if peak_tflops > 0 else None,
+                "fp64_pipe_active_pct_ncu": t["fp64_pipe_active_pct"], "source": t["source"].replace("gpurun_out/", "profiles/")}
     except Exception:
         return None
 

@@ -141,6 +141,39 @@ PRX_API int prx_react_box(
   const prx_array4* T, const prx_array4* rE, const prx_array4* rEsrc, const prx_array4* FC,
   const prx_array4i* mask, double dt, double time, void* cuda_stream);
 
+/* ---- several boxes in one call: the caller's MFIter loop (PC/Source/React.cpp:133-138, ReactEval main.cpp:484-526) ----
+ * lo / hi: [nboxes][3]; every array argument is an array of nboxes descriptors (mask may be NULL).  The boxes are independent;
+ * they are issued on internal streams and run concurrently, and `cuda_stream` waits for all of them (stream-ordered like
+ * prx_react_box: work queued on cuda_stream before the call completes first).  prx_last_react_return() covers all boxes. */
+PRX_API int prx_react_boxes(
+  prx_handle* h, int nboxes, const int* lo, const int* hi, const prx_array4* rY, const prx_array4* rYsrc,
+  const prx_array4* T, const prx_array4* rE, const prx_array4* rEsrc, const prx_array4* FC, const prx_array4i* mask,
+  double dt, double time, void* cuda_stream);
+
+/* ---- PeleC::react_state, the per-box body (PC/Source/React.cpp:140-343), fused around the reactor ----
+ * Replaces, for one box: the frcEExt kernel (React.cpp:181-220), the copies into STemp / extsrc_rY / extsrc_rE / fctCount /
+ * dummyMask (React.cpp:95-119), reactor->react (:222-228), the unpack kernel (:233-321: S_new, I_R[0..N]) and the heat-release
+ * kernel (:325-343: I_R[N+1]).  The integrator kernel reads S_old / S_new / non_react_src itself and writes S_new / I_R.
+ *   sold   S_old (react_init: pass S_new)                 NVAR components, read only
+ *   snew   S_new = S_old + dt*non_react_src on entry      NVAR components, updated iff do_update (= !react_init)
+ *   nonrs  non-reacting source terms                      NVAR components, read only
+ *   I_R    reaction source term, out                      NUM_SPECIES + 2 components (species, rho*E, heat release)
+ *   work   optional (NULL): the reactor's FC per cell     1 component
+ *   ix     component indices of the state vector (PC/Source/IndexDefines.H:3-12)
+ * Not supported: rotating-frame energy (pelec.do_rf; rotenrg = 0) and EB-covered boxes (the caller skips those, :151-158). */
+typedef struct prx_state_index {
+  int urho, umx, umy, umz, ueden, ueint, utemp, ufs, nvar;
+} prx_state_index;
+
+PRX_API int prx_react_state_box(
+  prx_handle* h, const int lo[3], const int hi[3], const prx_array4* sold, const prx_array4* snew, const prx_array4* nonrs,
+  const prx_array4* I_R, const prx_array4* work, const prx_state_index* ix, double dt, int do_update, void* cuda_stream);
+
+PRX_API int prx_react_state_boxes(
+  prx_handle* h, int nboxes, const int* lo, const int* hi, const prx_array4* sold, const prx_array4* snew,
+  const prx_array4* nonrs, const prx_array4* I_R, const prx_array4* work, const prx_state_index* ix, double dt,
+  int do_update, void* cuda_stream);
+
 /* ---- ReactorBase::react, flat version (ReactorBase.H:42-54), DEVICE pointers ----
  * y [ncells*(N+1)] YCOrder (cell-major, T last), ysrc [ncells*N], e [ncells], esrc [ncells].
  * Reference semantics of the 1-D call: T is taken from y (no initial REY2T) and the

@@ -326,3 +326,60 @@ def reacteval_states(lib, ncells_xyz, fuel=None):
     jj = np.tile(np.repeat(np.arange(ny), nx), nz)
     rY = (Y[:, None] * rho_j[jj][None, :])
     return BoxState(rY, Tj[jj], (rho_j * e_j)[jj])
+
+
+# ----------------------------------------------------------------------------------------------
+# PeleC::react_state body (test infrastructure; restated from PC/Source/React.cpp:181-343, numpy)
+# PARITY UNPINNED for the pack / unpack arithmetic: PeleC itself needs its cmake build system (not run here); the reactor
+# call in the middle is the pinned oracle.  Rotating-frame terms omitted (rotenrg = 0), as in the product.
+# ----------------------------------------------------------------------------------------------
+UIDX = dict(urho=0, umx=1, umy=2, umz=3, ueden=4, ueint=5, utemp=6, ufs=7)
+
+
+def react_state_oracle(orc, sold, snew, nonrs, dt, do_update=True, reactor="cvode", **kw):
+    """sold, snew, nonrs: [NVAR, ncells] arrays (NVAR = 7 + N).  Returns (snew_out, I_R [N+2, ncells], FC)."""
+    u = UIDX
+    N = orc.N
+    sold, snew, nonrs = (np.array(x, dtype=np.float64) for x in (sold, snew, nonrs))
+    nc = sold.shape[1]
+    # ---- React.cpp:181-220 (pack)
+    rhou, rhov, rhow, rho_old = sold[u["umx"]], sold[u["umy"]], sold[u["umz"]], sold[u["urho"]]
+    rhoInv = 1.0 / rho_old
+    e_old = (sold[u["ueden"]] - 0.5 * (rhou * rhou + rhov * rhov + rhow * rhow) * rhoInv) * rhoInv
+    rhou, rhov, rhow = snew[u["umx"]], snew[u["umy"]], snew[u["umz"]]
+    rhoInv = 1.0 / snew[u["urho"]]
+    rhoedot_ext = (snew[u["ueden"]] - 0.5 * (rhou * rhou + rhov * rhov + rhow * rhow) * rhoInv - rho_old * e_old) / dt
+    st = BoxState(sold[u["ufs"]:u["ufs"] + N].copy(), sold[u["utemp"]].copy(), sold[u["ueint"]].copy(),
+                  nonrs[u["ufs"]:u["ufs"] + N].copy(), rhoedot_ext.copy())
+    # ---- React.cpp:222-228 (reactor, current_time = 0)
+    if reactor == "cvode":
+        orc.react_cvode(st, dt, 0.0, **kw)
+    else:
+        orc.react_rk64(st, dt, 0.0, **kw)
+    # ---- React.cpp:233-321 (unpack, I_R)
+    umnew = sold[u["umx"]] + dt * nonrs[u["umx"]]
+    vmnew = sold[u["umy"]] + dt * nonrs[u["umy"]]
+    wmnew = sold[u["umz"]] + dt * nonrs[u["umz"]]
+    rhonew = np.zeros(nc)
+    for n in range(N):
+        rhonew = rhonew + st.rY[n]
+    out = snew.copy()
+    eint_new = rho_old * e_old + dt * rhoedot_ext
+    eden_new = eint_new + 0.5 * (umnew * umnew + vmnew * vmnew + wmnew * wmnew) / rhonew
+    if do_update:
+        out[u["urho"]], out[u["umx"]], out[u["umy"]], out[u["umz"]] = rhonew, umnew, vmnew, wmnew
+        out[u["ufs"]:u["ufs"] + N] = st.rY
+        out[u["utemp"]] = st.T
+        out[u["ueint"]] = eint_new
+        out[u["ueden"]] = eden_new
+    I_R = np.zeros((N + 2, nc))
+    for n in range(N):
+        I_R[n] = (st.rY[n] - sold[u["ufs"] + n]) / dt - nonrs[u["ufs"] + n]
+    I_R[N] = (eden_new - sold[u["ueden"]]) / dt - nonrs[u["ueden"]]
+    # ---- React.cpp:325-343 (heat release from the NEW state: RTY2Hi depends on T only)
+    Th = out[u["utemp"]]
+    Y = (out[u["ufs"]:u["ufs"] + N] / out[u["urho"]]).T.copy()
+    hi = orc.thermo(Th, Y)[3]  # [ncells, N] species enthalpies, mass units (CKHMS)
+    for n in range(N):
+        I_R[N + 1] -= hi[:, n] * I_R[n]
+    return out, I_R, st.FC

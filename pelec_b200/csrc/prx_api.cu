@@ -12,6 +12,7 @@
 #include "prx_kernels.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <nvtx3/nvToolsExt.h> // header-only (dlopens the injection library of an attached profiler; no link dependency)
 
 using namespace prx;
 
@@ -22,9 +23,9 @@ struct prx_handle
   int device;
   std::vector<double> typ_vals; // size N+1; typ_vals[0] <= 0: not set
   DevStats* d_stats;
-  int* d_queues; // ring of work-queue counters: one per in-flight launch
-  int n_queues;
-  std::atomic<unsigned> q_next; // several host threads may launch through one handle (different streams)
+  cudaStream_t box_streams[8];   // internal streams of the multi-box entry points (created on first use)
+  cudaEvent_t box_events[9];
+  int n_box_streams;
   std::mutex host_mutex;        // the *_host calls share one staging buffer: serialised per handle
   SchedParams sched;
   long long last_ncells;
@@ -92,13 +93,13 @@ struct DeviceGuard
   }
 };
 
-bool view_of(const prx_array4* a, const int lo[3], int need_comp, ArrView* v)
+bool view_of(const prx_array4* a, const int lo[3], int need_comp, ArrView* v, const int* hi = nullptr)
 {
   if (a == nullptr || a->p == nullptr || a->ncomp < need_comp) {
     return false;
   }
   for (int d = 0; d < 3; d++) {
-    if (lo[d] < a->begin[d]) {
+    if (lo[d] < a->begin[d] || (hi != nullptr && hi[d] >= a->end[d])) { // the box must lie inside the array (end is exclusive)
       return false;
     }
   }
@@ -110,9 +111,15 @@ bool view_of(const prx_array4* a, const int lo[3], int need_comp, ArrView* v)
   return true;
 }
 
-int* next_queue(prx_handle* h)
+// One work-queue counter per launch, from the stream-ordered pool of the launch's stream: released (cudaFreeAsync) behind
+// the kernel, so two launches in flight - on whatever streams - never share a counter.
+int* new_queue(cudaStream_t stream)
 {
-  int* q = h->d_queues + (h->q_next.fetch_add(1u) % (unsigned)h->n_queues);
+  int* q = nullptr;
+  if (cudaMallocAsync((void**)&q, sizeof(int), stream) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
   return q;
 }
 
@@ -304,9 +311,7 @@ int prx_create(const prx_config* cfg, prx_handle** out)
   h->device = dev;
   h->typ_vals.assign(ops->num_species + 1, -1.0);
   h->d_stats = nullptr;
-  h->d_queues = nullptr;
-  h->n_queues = 256;
-  h->q_next.store(0u);
+  h->n_box_streams = 0;
   h->sched.jac_defer_min_lanes = env_int("PRX_JAC_DEFER", 1);
   h->sched.lu_defer_min_lanes = env_int("PRX_LU_DEFER", 1);
   h->sched.bdf_variant = env_int("PRX_BDF_VARIANT", -1);
@@ -337,7 +342,6 @@ int prx_create(const prx_config* cfg, prx_handle** out)
     cudaGetLastError();
   }
   if (cudaMalloc(&h->d_stats, sizeof(DevStats)) != cudaSuccess ||
-      cudaMalloc(&h->d_queues, sizeof(int) * h->n_queues) != cudaSuccess ||
       cudaMemset(h->d_stats, 0, sizeof(DevStats)) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->stage_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -360,8 +364,12 @@ int prx_destroy(prx_handle* h)
   if (h->d_stats) {
     cudaFree(h->d_stats);
   }
-  if (h->d_queues) {
-    cudaFree(h->d_queues);
+  for (int i = 0; i < h->n_box_streams; i++) {
+    cudaStreamDestroy(h->box_streams[i]);
+    cudaEventDestroy(h->box_events[i]);
+  }
+  if (h->n_box_streams > 0) {
+    cudaEventDestroy(h->box_events[8]);
   }
   if (h->d_stage) {
     cudaFree(h->d_stage);
@@ -414,6 +422,12 @@ __global__ void order_keys_kernel(const BoxArgs a, const int neq, float* __restr
     const int j = r % a.len[1];
     const int k = r / a.len[1];
     T = a.T.p[(long long)i + (long long)j * a.T.js + (long long)k * a.T.ks];
+  } else if (a.layout == LAYOUT_STATE) {
+    const int i = c % a.len[0];
+    const int r = c / a.len[0];
+    const int j = r % a.len[1];
+    const int k = r / a.len[1];
+    T = a.sold.p[(long long)i + (long long)j * a.sold.js + (long long)k * a.sold.ks + (long long)a.ix.utemp * a.sold.ns];
   } else {
     T = a.y[(long long)c * neq + (neq - 1)];
   }
@@ -456,15 +470,23 @@ static cudaError_t build_order(const BoxArgs& a, int neq, cudaStream_t stream, v
   return cudaSuccess;
 }
 
+// one NVTX range per react call (the reference wraps react in BL_PROFILE("Pele::ReactorCvode::react()"))
+struct NvtxRange
+{
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 static int react_args(prx_handle* h, const BoxArgs& a, cudaStream_t stream)
 {
+  NvtxRange nvtx(h->cfg.reactor_kind == PRX_REACTOR_RK64 ? "prx::ReactorRK64::react" : "prx::ReactorCvode::react");
   DeviceGuard g(h->device);
   // per-launch step sum (for the value ReactorBase::react returns)
   if (!h->keep_last_steps) {
     PRX_CUDA(h, cudaMemsetAsync(&h->d_stats->v[ST_LAST_STEPS], 0, 2 * sizeof(unsigned long long), stream)); // + ST_LAST_MAXRHS
     h->last_ncells = 0;
-    h->last_layout = a.layout;
   }
+  h->last_layout = a.layout;
   h->last_ncells += a.ncells;
   cudaError_t e;
   BoxArgs b = a;
@@ -480,11 +502,19 @@ static int react_args(prx_handle* h, const BoxArgs& a, cudaStream_t stream)
   if (sp.refill_min < 0) { // default: batch the refills of a warp only when the cells arrive unsorted
     sp.refill_min = (b.order != nullptr) ? 1 : 16;
   }
-  if (h->cfg.reactor_kind == PRX_REACTOR_RK64) {
-    e = h->ops->launch_rk64(b, h->cfg, next_queue(h), h->d_stats, stream);
-  } else {
-    e = h->ops->launch_bdf(b, h->cfg, h->typ_vals.data(), next_queue(h), h->d_stats, sp, stream);
+  int* queue = new_queue(stream);
+  if (queue == nullptr) {
+    if (order_block != nullptr) {
+      cudaFreeAsync(order_block, stream);
+    }
+    return fail(h, PRX_ERR_ALLOC, "work-queue counter");
   }
+  if (h->cfg.reactor_kind == PRX_REACTOR_RK64) {
+    e = h->ops->launch_rk64(b, h->cfg, queue, h->d_stats, stream);
+  } else {
+    e = h->ops->launch_bdf(b, h->cfg, h->typ_vals.data(), queue, h->d_stats, sp, stream);
+  }
+  cudaFreeAsync(queue, stream);
   if (order_block != nullptr) {
     cudaFreeAsync(order_block, stream); // stream-ordered: released after the integrator kernel
   }
@@ -521,11 +551,16 @@ int prx_react_box(
     return fail(h, PRX_ERR_BAD_ARG, "box too large (int32 cell index)");
   }
   a.ncells = (int)nc;
-  if (!view_of(rY, lo, N, &a.rY) || !view_of(rYsrc, lo, N, &a.rYsrc) || !view_of(T, lo, 1, &a.T) ||
-      !view_of(rE, lo, 1, &a.rE) || !view_of(rEsrc, lo, 1, &a.rEsrc) || !view_of(FC, lo, 1, &a.FC)) {
+  if (!view_of(rY, lo, N, &a.rY, hi) || !view_of(rYsrc, lo, N, &a.rYsrc, hi) || !view_of(T, lo, 1, &a.T, hi) ||
+      !view_of(rE, lo, 1, &a.rE, hi) || !view_of(rEsrc, lo, 1, &a.rEsrc, hi) || !view_of(FC, lo, 1, &a.FC, hi)) {
     return fail(h, PRX_ERR_BAD_ARG, "prx_react_box: null/short Array4 or box outside the array");
   }
   if (mask != nullptr && mask->p != nullptr) {
+    for (int d = 0; d < 3; d++) {
+      if (lo[d] < mask->begin[d] || hi[d] >= mask->end[d] || mask->ncomp < 1) {
+        return fail(h, PRX_ERR_BAD_ARG, "prx_react_box: box outside the mask array");
+      }
+    }
     a.mask.js = mask->jstride;
     a.mask.ks = mask->kstride;
     a.mask.ns = mask->nstride;
@@ -535,6 +570,204 @@ int prx_react_box(
   a.dt = dt;
   a.time = time;
   return react_args(h, a, (cudaStream_t)cuda_stream);
+}
+
+// ---- fused PeleC::react_state body (PC/Source/React.cpp:181-343) -----------------------------------------------
+static int react_state_one(
+  prx_handle* h, const int lo[3], const int hi[3], const prx_array4* sold, const prx_array4* snew, const prx_array4* nonrs,
+  const prx_array4* I_R, const prx_array4* work, const prx_state_index* ix, double dt, int do_update, cudaStream_t stream)
+{
+  const int N = h->ops->num_species;
+  if (ix->nvar < ix->ufs + N || ix->urho < 0 || ix->ufs < 0) {
+    return fail(h, PRX_ERR_BAD_ARG, "prx_react_state_box: state index table does not fit NUM_SPECIES");
+  }
+  BoxArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.layout = LAYOUT_STATE;
+  long long nc = 1;
+  for (int d = 0; d < 3; d++) {
+    a.len[d] = hi[d] - lo[d] + 1;
+    if (a.len[d] <= 0) {
+      return PRX_OK; // empty box
+    }
+    nc *= a.len[d];
+  }
+  if (nc > 2147483647LL) {
+    return fail(h, PRX_ERR_BAD_ARG, "box too large (int32 cell index)");
+  }
+  a.ncells = (int)nc;
+  if (!view_of(sold, lo, ix->nvar, &a.sold, hi) || !view_of(snew, lo, ix->nvar, &a.snew, hi) ||
+      !view_of(nonrs, lo, ix->nvar, &a.nonrs, hi) || !view_of(I_R, lo, N + 2, &a.IR, hi)) {
+    return fail(h, PRX_ERR_BAD_ARG, "prx_react_state_box: null/short Array4 or box outside the array");
+  }
+  if (work != nullptr && work->p != nullptr && !view_of(work, lo, 1, &a.FC, hi)) {
+    return fail(h, PRX_ERR_BAD_ARG, "prx_react_state_box: box outside the work array");
+  }
+  a.ix.urho = ix->urho;
+  a.ix.umx = ix->umx;
+  a.ix.umy = ix->umy;
+  a.ix.umz = ix->umz;
+  a.ix.ueden = ix->ueden;
+  a.ix.ueint = ix->ueint;
+  a.ix.utemp = ix->utemp;
+  a.ix.ufs = ix->ufs;
+  a.do_update = do_update;
+  a.dt = dt;
+  a.time = 0.0; // React.cpp:171: current_time = 0
+  const bool fused = (h->cfg.reactor_kind == PRX_REACTOR_RK64) || h->ops->bdf_is_fused(h->sched);
+  if (fused) {
+    return react_args(h, a, stream);
+  }
+  // unfused form (cooperative kernel): pack -> Array4 react on stream-ordered scratch -> unpack; still one call, no
+  // MultiFab temporaries on the caller's side.  Scratch = [rY N | T | rE | rEsrc | FC] x ncells doubles.
+  DeviceGuard g(h->device);
+  double* scratch = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&scratch, sizeof(double) * (size_t)(N + 4) * (size_t)nc, stream);
+  if (e != cudaSuccess) {
+    return fail(h, PRX_ERR_ALLOC, "react_state scratch", e);
+  }
+  auto sv = [&](double* p) {
+    ArrView v;
+    v.p = p;
+    v.js = a.len[0];
+    v.ks = (long long)a.len[0] * a.len[1];
+    v.ns = nc;
+    return v;
+  };
+  a.rY = sv(scratch);
+  a.T = sv(scratch + (size_t)N * nc);
+  a.rE = sv(scratch + (size_t)(N + 1) * nc);
+  a.rEsrc = sv(scratch + (size_t)(N + 2) * nc);
+  if (a.FC.p == nullptr) {
+    a.FC = sv(scratch + (size_t)(N + 3) * nc);
+  }
+  a.rYsrc = a.nonrs; // the species rows of the non-reacting source, in place (read only)
+  a.rYsrc.p += (long long)ix->ufs * a.nonrs.ns;
+  int rc = PRX_OK;
+  e = h->ops->state_pack(a, stream);
+  if (e == cudaSuccess) {
+    BoxArgs b = a;
+    b.layout = LAYOUT_ARRAY4;
+    rc = react_args(h, b, stream);
+    if (rc == PRX_OK) {
+      e = h->ops->state_unpack(a, h->cfg, stream);
+    }
+  }
+  cudaFreeAsync(scratch, stream);
+  if (rc != PRX_OK) {
+    return rc;
+  }
+  return e == cudaSuccess ? PRX_OK : fail(h, PRX_ERR_CUDA, "react_state pack/unpack", e);
+}
+
+int prx_react_state_box(
+  prx_handle* h, const int lo[3], const int hi[3], const prx_array4* sold, const prx_array4* snew, const prx_array4* nonrs,
+  const prx_array4* I_R, const prx_array4* work, const prx_state_index* ix, double dt, int do_update, void* cuda_stream)
+{
+  if (h == nullptr || lo == nullptr || hi == nullptr || ix == nullptr) {
+    return PRX_ERR_BAD_ARG;
+  }
+  return react_state_one(h, lo, hi, sold, snew, nonrs, I_R, work, ix, dt, do_update, (cudaStream_t)cuda_stream);
+}
+
+// ---- multi-box entry points: the MFIter loop of the caller (PC/Source/React.cpp:133-138) in one call ------------------
+// PeleC hands the reactor 16^3 - 64^3 boxes; a single small box cannot fill 148 SMs and its latency is the critical path of
+// its slowest cell.  The boxes of one call are independent, so they are issued round-robin on internal streams (as AMReX does
+// with amrex.max_gpu_streams) and run concurrently; the caller's stream waits for all of them.
+static int box_fanout_begin(prx_handle* h, cudaStream_t user, int nboxes, int* nstreams)
+{
+  DeviceGuard g(h->device);
+  int want = env_int("PRX_BOX_STREAMS", 8);
+  want = want < 1 ? 1 : (want > 8 ? 8 : want);
+  while (h->n_box_streams < want) {
+    const int i = h->n_box_streams;
+    if (i == 0) {
+      PRX_CUDA(h, cudaEventCreateWithFlags(&h->box_events[8], cudaEventDisableTiming));
+    }
+    PRX_CUDA(h, cudaStreamCreateWithFlags(&h->box_streams[i], cudaStreamNonBlocking));
+    PRX_CUDA(h, cudaEventCreateWithFlags(&h->box_events[i], cudaEventDisableTiming));
+    h->n_box_streams++;
+  }
+  *nstreams = nboxes < want ? nboxes : want;
+  PRX_CUDA(h, cudaEventRecord(h->box_events[8], user)); // the boxes start after the work already queued on the caller's stream
+  for (int i = 0; i < *nstreams; i++) {
+    PRX_CUDA(h, cudaStreamWaitEvent(h->box_streams[i], h->box_events[8], 0));
+  }
+  return PRX_OK;
+}
+
+static int box_fanout_end(prx_handle* h, cudaStream_t user, int nstreams)
+{
+  DeviceGuard g(h->device);
+  for (int i = 0; i < nstreams; i++) {
+    PRX_CUDA(h, cudaEventRecord(h->box_events[i], h->box_streams[i]));
+    PRX_CUDA(h, cudaStreamWaitEvent(user, h->box_events[i], 0));
+  }
+  return PRX_OK;
+}
+
+int prx_react_boxes(
+  prx_handle* h, int nboxes, const int* lo, const int* hi, const prx_array4* rY, const prx_array4* rYsrc, const prx_array4* T,
+  const prx_array4* rE, const prx_array4* rEsrc, const prx_array4* FC, const prx_array4i* mask, double dt, double time,
+  void* cuda_stream)
+{
+  if (h == nullptr || nboxes < 0 || (nboxes > 0 && (!lo || !hi || !rY || !rYsrc || !T || !rE || !rEsrc || !FC))) {
+    return PRX_ERR_BAD_ARG;
+  }
+  if (nboxes == 0) {
+    return PRX_OK;
+  }
+  std::lock_guard<std::mutex> lock(h->host_mutex); // the internal streams / events belong to the handle
+  int ns = 1;
+  {
+    // the per-call counters are reset once, on the caller's stream, BEFORE the fan-out event: every box accumulates into them
+    DeviceGuard g(h->device);
+    PRX_CUDA(h, cudaMemsetAsync(&h->d_stats->v[ST_LAST_STEPS], 0, 2 * sizeof(unsigned long long), (cudaStream_t)cuda_stream));
+    h->last_ncells = 0;
+  }
+  int rc = box_fanout_begin(h, (cudaStream_t)cuda_stream, nboxes, &ns);
+  bool keep = true;
+  for (int b = 0; b < nboxes && rc == PRX_OK; b++) {
+    h->keep_last_steps = keep;
+    rc = prx_react_box(h, lo + 3 * b, hi + 3 * b, rY + b, rYsrc + b, T + b, rE + b, rEsrc + b, FC + b,
+                       mask != nullptr ? mask + b : nullptr, dt, time, h->box_streams[b % ns]);
+    keep = true;
+  }
+  h->keep_last_steps = false;
+  const int rc2 = box_fanout_end(h, (cudaStream_t)cuda_stream, ns);
+  return rc != PRX_OK ? rc : rc2;
+}
+
+int prx_react_state_boxes(
+  prx_handle* h, int nboxes, const int* lo, const int* hi, const prx_array4* sold, const prx_array4* snew,
+  const prx_array4* nonrs, const prx_array4* I_R, const prx_array4* work, const prx_state_index* ix, double dt, int do_update,
+  void* cuda_stream)
+{
+  if (h == nullptr || nboxes < 0 || ix == nullptr || (nboxes > 0 && (!lo || !hi || !sold || !snew || !nonrs || !I_R))) {
+    return PRX_ERR_BAD_ARG;
+  }
+  if (nboxes == 0) {
+    return PRX_OK;
+  }
+  std::lock_guard<std::mutex> lock(h->host_mutex);
+  int ns = 1;
+  {
+    // the per-call counters are reset once, on the caller's stream, BEFORE the fan-out event: every box accumulates into them
+    DeviceGuard g(h->device);
+    PRX_CUDA(h, cudaMemsetAsync(&h->d_stats->v[ST_LAST_STEPS], 0, 2 * sizeof(unsigned long long), (cudaStream_t)cuda_stream));
+    h->last_ncells = 0;
+  }
+  int rc = box_fanout_begin(h, (cudaStream_t)cuda_stream, nboxes, &ns);
+  bool keep = true;
+  for (int b = 0; b < nboxes && rc == PRX_OK; b++) {
+    h->keep_last_steps = keep;
+    rc = react_state_one(h, lo + 3 * b, hi + 3 * b, sold + b, snew + b, nonrs + b, I_R + b, work != nullptr ? work + b : nullptr,
+                         ix, dt, do_update, h->box_streams[b % ns]);
+    keep = true;
+  }
+  h->keep_last_steps = false;
+  const int rc2 = box_fanout_end(h, (cudaStream_t)cuda_stream, ns);
+  return rc != PRX_OK ? rc : rc2;
 }
 
 int prx_react_flat(
@@ -642,20 +875,29 @@ int prx_react_box_host(
       (size_t)ncomp, kind, strm);
   };
   int rc_react = PRX_OK;
+  // an error inside the pipeline must not return before the three streams are drained and the events destroyed
+  // (the async copies still touch the caller's host buffers): record it and fall through to the common exit
+#define SLAB_CUDA(call)                                        \
+  do {                                                         \
+    const cudaError_t e_ = (call);                             \
+    if (e_ != cudaSuccess && rc_react == PRX_OK) {             \
+      rc_react = fail(h, PRX_ERR_CUDA, #call, e_);             \
+    }                                                          \
+  } while (0)
   h->keep_last_steps = false;
   for (int sidx = 0; sidx < nslab && rc_react == PRX_OK; sidx++) {
     const int k0 = (int)((long long)nz * sidx / nslab), k1 = (int)((long long)nz * (sidx + 1) / nslab);
     const long long off = plane * k0, cells = plane * (k1 - k0);
-    PRX_CUDA(h, copy2d(d_rY, rY, sizeof(double), off, cells, N, cudaMemcpyHostToDevice, h->in_stream));
-    PRX_CUDA(h, copy2d(d_rYsrc, rYsrc, sizeof(double), off, cells, N, cudaMemcpyHostToDevice, h->in_stream));
-    PRX_CUDA(h, copy2d(d_T, T, sizeof(double), off, cells, 1, cudaMemcpyHostToDevice, h->in_stream));
-    PRX_CUDA(h, copy2d(d_rE, rE, sizeof(double), off, cells, 1, cudaMemcpyHostToDevice, h->in_stream));
-    PRX_CUDA(h, copy2d(d_rEsrc, rEsrc, sizeof(double), off, cells, 1, cudaMemcpyHostToDevice, h->in_stream));
+    SLAB_CUDA(copy2d(d_rY, rY, sizeof(double), off, cells, N, cudaMemcpyHostToDevice, h->in_stream));
+    SLAB_CUDA(copy2d(d_rYsrc, rYsrc, sizeof(double), off, cells, N, cudaMemcpyHostToDevice, h->in_stream));
+    SLAB_CUDA(copy2d(d_T, T, sizeof(double), off, cells, 1, cudaMemcpyHostToDevice, h->in_stream));
+    SLAB_CUDA(copy2d(d_rE, rE, sizeof(double), off, cells, 1, cudaMemcpyHostToDevice, h->in_stream));
+    SLAB_CUDA(copy2d(d_rEsrc, rEsrc, sizeof(double), off, cells, 1, cudaMemcpyHostToDevice, h->in_stream));
     if (mask != nullptr) {
-      PRX_CUDA(h, copy2d(d_mask, mask, sizeof(int), off, cells, 1, cudaMemcpyHostToDevice, h->in_stream));
+      SLAB_CUDA(copy2d(d_mask, mask, sizeof(int), off, cells, 1, cudaMemcpyHostToDevice, h->in_stream));
     }
-    PRX_CUDA(h, cudaEventRecord(ev_in[sidx], h->in_stream));
-    PRX_CUDA(h, cudaStreamWaitEvent(st, ev_in[sidx], 0));
+    SLAB_CUDA(cudaEventRecord(ev_in[sidx], h->in_stream));
+    SLAB_CUDA(cudaStreamWaitEvent(st, ev_in[sidx], 0));
     const int lo[3] = {0, 0, k0};
     const int hi[3] = {nx - 1, ny - 1, k1 - 1};
     rc_react = prx_react_box(h, lo, hi, &a_rY, &a_rYsrc, &a_T, &a_rE, &a_rEsrc, &a_FC, &a_mask, dt, time, st);
@@ -663,13 +905,14 @@ int prx_react_box_host(
     if (rc_react != PRX_OK) {
       break;
     }
-    PRX_CUDA(h, cudaEventRecord(ev_done[sidx], st));
-    PRX_CUDA(h, cudaStreamWaitEvent(h->out_stream, ev_done[sidx], 0));
-    PRX_CUDA(h, copy2d(rY, d_rY, sizeof(double), off, cells, N, cudaMemcpyDeviceToHost, h->out_stream));
-    PRX_CUDA(h, copy2d(T, d_T, sizeof(double), off, cells, 1, cudaMemcpyDeviceToHost, h->out_stream));
-    PRX_CUDA(h, copy2d(rE, d_rE, sizeof(double), off, cells, 1, cudaMemcpyDeviceToHost, h->out_stream));
-    PRX_CUDA(h, copy2d(FC, d_FC, sizeof(double), off, cells, 1, cudaMemcpyDeviceToHost, h->out_stream));
+    SLAB_CUDA(cudaEventRecord(ev_done[sidx], st));
+    SLAB_CUDA(cudaStreamWaitEvent(h->out_stream, ev_done[sidx], 0));
+    SLAB_CUDA(copy2d(rY, d_rY, sizeof(double), off, cells, N, cudaMemcpyDeviceToHost, h->out_stream));
+    SLAB_CUDA(copy2d(T, d_T, sizeof(double), off, cells, 1, cudaMemcpyDeviceToHost, h->out_stream));
+    SLAB_CUDA(copy2d(rE, d_rE, sizeof(double), off, cells, 1, cudaMemcpyDeviceToHost, h->out_stream));
+    SLAB_CUDA(copy2d(FC, d_FC, sizeof(double), off, cells, 1, cudaMemcpyDeviceToHost, h->out_stream));
   }
+#undef SLAB_CUDA
   h->keep_last_steps = false;
   cudaError_t es = cudaStreamSynchronize(h->out_stream);
   cudaError_t es2 = cudaStreamSynchronize(st);
@@ -913,6 +1156,7 @@ int prx_probe_rhs_host(
   if (h == nullptr || n <= 0 || !y || !rhoe || !rhoesrc || !rYsrc || !ydot) {
     return PRX_ERR_BAD_ARG;
   }
+  std::lock_guard<std::mutex> host_lock(h->host_mutex);
   DeviceGuard g(h->device);
   const int N = h->ops->num_species, NEQ = N + 1;
   const size_t nd = (size_t)n * (2 * NEQ + N + 2);
@@ -941,6 +1185,7 @@ int prx_probe_jac_host(prx_handle* h, int n, const double* y, double* J)
   if (h == nullptr || n <= 0 || !y || !J) {
     return PRX_ERR_BAD_ARG;
   }
+  std::lock_guard<std::mutex> host_lock(h->host_mutex);
   DeviceGuard g(h->device);
   const int N = h->ops->num_species, NEQ = N + 1;
   const size_t nd = (size_t)n * (NEQ + (size_t)NEQ * NEQ);

@@ -36,13 +36,16 @@
 // Transcendentals of the generated straight-line code (gen.py redirects exp / log / log10 here).
 // ncu, round 1 (profiles/r01n_ncu_bdf_lidryer_64_by_line.txt): libm's exp was 27 % and log10 8 % of ALL executed
 // instructions of the BDF kernel - 44 instructions per exp of which 26 are UMOV pairs for its 13 literals, 146 per log10.
-//  * prx_exp: the same algorithm and coefficients as the library's fast path (argument reduction with a two-part ln 2, degree-11
-//    polynomial, exponent patched into the high word; 0.90 ulp max on [-708, 708] measured against expl on the host), but its
-//    literals come from a __constant__ table (one LDCU.128 per two of them).  Arguments outside the fast range (the reference's
-//    exp(-T*1e30) Troe terms, overflow, NaN) take the library path.
+//  * prx_exp (PRX_CUSTOM_MATH=1): the same algorithm and coefficients as the library's fast path (argument reduction with a
+//    two-part ln 2, degree-11 polynomial, exponent patched into the high word; 0.90 ulp max on [-708, 708] measured against
+//    expl on the host), literals from a __constant__ table (one LDCU.128 per two).  Arguments outside the fast range (the
+//    reference's exp(-T*1e30) Troe terms, overflow, NaN) take the library path.
 //  * prx_log10 = log(x) * log10(e): <= 1.5 ulp instead of the library's 1 ulp, 41 instructions instead of 146.
+// Measured (session r02d, 128^3 LiDryer): BDF 66.4 vs 66.7 ms, RK64 92.7 vs 90.9 ms - no gain: a single out-of-line exp is a
+// chain of 13 dependent DFMAs whose latency, not its instruction count, is what the warp waits for.  OFF by default (the
+// library functions keep the round-1 parity numbers); kept for the batched-evaluation experiment.
 #ifndef PRX_CUSTOM_MATH
-#define PRX_CUSTOM_MATH 1
+#define PRX_CUSTOM_MATH 0
 #endif
 #if defined(PRX_NOINLINE_MATH)
 #define PRX_MATHFN static __device__ __noinline__
@@ -87,6 +90,59 @@ PRX_MATHFN double prx_log(const double x) { return log(x); }
 PRX_MATHFN double prx_log10(const double x) { return log10(x); }
 #endif
 #define PRX_MATH_REDIRECT 1
+#endif
+
+// ---- paired exponentials (gen.py emits PRX_EXP2(a, b) for the two independent exp() of a reversible reaction) -----------------
+struct prx_d2
+{
+  double x, y;
+};
+#ifndef PRX_BATCH_EXP
+#define PRX_BATCH_EXP 1
+#endif
+#if !defined(PRX_HOST_TEST) && PRX_BATCH_EXP
+// Both chains of the library's fast-path algorithm (see prx_exp above: same reduction, same degree-11 polynomial, same
+// coefficients) advance in lock step, so that every DFMA has an independent neighbour to hide its latency behind; literals
+// are materialised once for the two values.  Arguments outside [-708, 708] / NaN: library path for both.
+static __device__ __noinline__ prx_d2 prx_exp2(const double xa, const double xb)
+{
+  prx_d2 r;
+  if (!(fabs(xa) <= 708.0) || !(fabs(xb) <= 708.0)) {
+    r.x = exp(xa);
+    r.y = exp(xb);
+    return r;
+  }
+  double ta = fma(xa, 1.4426950408889634, 6755399441055744.0);
+  double tb = fma(xb, 1.4426950408889634, 6755399441055744.0);
+  const int ia = __double2loint(ta), ib = __double2loint(tb);
+  ta -= 6755399441055744.0;
+  tb -= 6755399441055744.0;
+  double a = fma(ta, -6.9314718055994529e-01, xa), b = fma(tb, -6.9314718055994529e-01, xb);
+  a = fma(ta, -2.3190468138462996e-17, a);
+  b = fma(tb, -2.3190468138462996e-17, b);
+  double p = 2.5052097064908941e-08, q = 2.5052097064908941e-08;
+#define PRX_E2(c)      \
+  p = fma(p, a, (c)); \
+  q = fma(q, b, (c));
+  PRX_E2(2.7626262793835868e-07)
+  PRX_E2(2.7557414788000726e-06)
+  PRX_E2(2.4801504602132958e-05)
+  PRX_E2(1.9841269707468915e-04)
+  PRX_E2(1.3888888932258898e-03)
+  PRX_E2(8.3333333333978320e-03)
+  PRX_E2(4.1666666666573905e-02)
+  PRX_E2(1.6666666666666563e-01)
+  PRX_E2(5.0000000000000056e-01)
+  PRX_E2(1.0)
+  PRX_E2(1.0)
+#undef PRX_E2
+  r.x = __hiloint2double(__double2hiint(p) + (ia << 20), __double2loint(p));
+  r.y = __hiloint2double(__double2hiint(q) + (ib << 20), __double2loint(q));
+  return r;
+}
+#define PRX_EXP2(a, b) prx_exp2((a), (b))
+#else
+#define PRX_EXP2(a, b) (prx_d2{exp(a), exp(b)})
 #endif
 
 #include PRX_MECH_HEADER

@@ -531,10 +531,53 @@ PRX_DEV void bdf_adjust_order(Cell& s, const int deltaq, const int qmax)
   }
 }
 
+// cvPredict / cvRestore (cvode.c:2687-2717, 3386-3401): zn[j-1] +/-= zn[j] for k = 1..q, j = q..k.  Per component the q+1
+// Nordsieck entries are loaded once, the triangle of additions runs in registers in the reference's order, and q entries are
+// stored: 2q+1 memory accesses per component instead of 3q(q+1)/2 (ncu r02a: the statement-by-statement form was 11.8 % of
+// the gen-1 kernel's local-memory traffic).  Measured on B200 (session r02f): SLOWER, 70.6 vs 67.0 ms per 128^3 LiDryer - the
+// statement form keeps 10 independent loads in flight per statement, the register form serialises them behind its triangle;
+// kept behind PRX_PASCAL_PREDICT (off) and bit-identical (tests/test_host_logic.py passes with either).
+template <class Cell, int SIGN>
+PRX_DEV void bdf_pascal(Cell& s)
+{
+  const int q = s.q;
+  PRX_VEC_FOR(i) {
+    double z[LMAX];
+    PRX_UNROLL
+    for (int j = 0; j < LMAX; j++) {
+      z[j] = 0.0;
+      if (j <= q) {
+        z[j] = s.zn(j)[i];
+      }
+    }
+    PRX_UNROLL
+    for (int k = 1; k < LMAX; k++) {
+      PRX_UNROLL
+      for (int j = LMAX - 1; j >= k; j--) {
+        if (j <= q) { // (k <= j)
+          z[j - 1] = (SIGN > 0) ? (z[j - 1] + z[j]) : (z[j - 1] - z[j]);
+        }
+      }
+    }
+    PRX_UNROLL
+    for (int j = 0; j < LMAX - 1; j++) {
+      if (j < q) {
+        s.zn(j)[i] = z[j];
+      }
+    }
+  }
+}
+
+#ifndef PRX_PASCAL_PREDICT
+#define PRX_PASCAL_PREDICT 0 // measured (session r02f, 128^3 LiDryer): 70.6 ms with the register form vs 67.0 ms with the statement form
+#endif
 template <class Cell>
 PRX_DEV void bdf_predict(Cell& s)
 {
   s.tn += s.h;
+#if PRX_PASCAL_PREDICT
+  bdf_pascal<Cell, 1>(s);
+#else
   for (int k = 1; k <= s.q; k++) {
     for (int j = s.q; j >= k; j--) {
       PRX_VEC_FOR(i) {
@@ -542,12 +585,16 @@ PRX_DEV void bdf_predict(Cell& s)
       }
     }
   }
+#endif
 }
 
 template <class Cell>
 PRX_DEV void bdf_restore(Cell& s)
 {
   s.tn = s.saved_t;
+#if PRX_PASCAL_PREDICT
+  bdf_pascal<Cell, -1>(s);
+#else
   for (int k = 1; k <= s.q; k++) {
     for (int j = s.q; j >= k; j--) {
       PRX_VEC_FOR(i) {
@@ -555,6 +602,7 @@ PRX_DEV void bdf_restore(Cell& s)
       }
     }
   }
+#endif
 }
 
 // cvSet -> cvSetBDF -> cvSetTqBDF (cvode.c:2730-2999)

@@ -132,6 +132,90 @@ __device__ __forceinline__ long long cell_offset(const int c, const int* len, co
   return (long long)i + (long long)j * js + (long long)k * ks;
 }
 
+// ---- fused PeleC::react_state body (PC/Source/React.cpp:181-343), one cell ---------------------------------
+// Pack (React.cpp:181-220): the reactor integrates from the OLD state (rhoY, T, rho*e_int of S_old) with the non-reacting
+// species sources and the energy source rhoedot_ext = (rho*e_int implied by S_new = S_old + dt*sources  -  rho_old*e_old) / dt.
+// Rotating-frame energy (pelec.do_rf) is not supported: rotenrg = 0 (adding it is exact-zero arithmetic in the reference).
+__device__ __forceinline__ double state_e_old(const BoxArgs& a, const long long oo, double& rho_old)
+{
+  const double* so = a.sold.p + oo;
+  const long long ns = a.sold.ns;
+  const double rhou = so[a.ix.umx * ns], rhov = so[a.ix.umy * ns], rhow = so[a.ix.umz * ns];
+  rho_old = so[a.ix.urho * ns];
+  const double rhoInv = 1.0 / rho_old;
+  return (so[a.ix.ueden * ns] - 0.5 * (rhou * rhou + rhov * rhov + rhow * rhow) * rhoInv) * rhoInv;
+}
+
+__device__ __forceinline__ double state_rhoedot_ext(const BoxArgs& a, const int c)
+{
+  double rho_old;
+  const double e_old = state_e_old(a, cell_offset(c, a.len, a.sold.js, a.sold.ks), rho_old);
+  const double* sn = a.snew.p + cell_offset(c, a.len, a.snew.js, a.snew.ks);
+  const long long ns = a.snew.ns;
+  const double rhou = sn[a.ix.umx * ns], rhov = sn[a.ix.umy * ns], rhow = sn[a.ix.umz * ns];
+  const double rhoInv = 1.0 / sn[a.ix.urho * ns];
+  return (sn[a.ix.ueden * ns] - 0.5 * (rhou * rhou + rhov * rhov + rhow * rhow) * rhoInv - rho_old * e_old) / a.dt;
+}
+
+// Unpack + I_R + heat release (React.cpp:233-343) from the reactor's output (rhoY_new[N], T_new) of one cell.
+__device__ __forceinline__ void state_unpack(
+  const BoxArgs& a, const int c, const double* rhoY, const double Tnew, const double rhoedot_ext, const double fc)
+{
+  const long long oo = cell_offset(c, a.len, a.sold.js, a.sold.ks);
+  const long long on = cell_offset(c, a.len, a.snew.js, a.snew.ks);
+  const long long os = cell_offset(c, a.len, a.nonrs.js, a.nonrs.ks);
+  const long long oi = cell_offset(c, a.len, a.IR.js, a.IR.ks);
+  const double* so = a.sold.p + oo;
+  const double* nr = a.nonrs.p + os;
+  double* sn = a.snew.p + on;
+  double* ir = a.IR.p + oi;
+  const long long sos = a.sold.ns, nrs = a.nonrs.ns, sns = a.snew.ns, irs = a.IR.ns;
+  const double dt = a.dt;
+  double rho_old;
+  const double e_old = state_e_old(a, oo, rho_old);
+  const double umnew = so[a.ix.umx * sos] + dt * nr[a.ix.umx * nrs];
+  const double vmnew = so[a.ix.umy * sos] + dt * nr[a.ix.umy * nrs];
+  const double wmnew = so[a.ix.umz * sos] + dt * nr[a.ix.umz * nrs];
+  double rhonew = 0.0;
+#pragma unroll
+  for (int n = 0; n < N; n++) {
+    rhonew += rhoY[n];
+  }
+  const double eint_new = rho_old * e_old + dt * rhoedot_ext;
+  const double eden_new = eint_new + 0.5 * (umnew * umnew + vmnew * vmnew + wmnew * wmnew) / rhonew;
+  double T_h = Tnew;
+  if (a.do_update) {
+    sn[a.ix.urho * sns] = rhonew;
+    sn[a.ix.umx * sns] = umnew;
+    sn[a.ix.umy * sns] = vmnew;
+    sn[a.ix.umz * sns] = wmnew;
+#pragma unroll
+    for (int n = 0; n < N; n++) {
+      sn[(a.ix.ufs + n) * sns] = rhoY[n];
+    }
+    sn[a.ix.utemp * sns] = Tnew;
+    sn[a.ix.ueint * sns] = eint_new;
+    sn[a.ix.ueden * sns] = eden_new;
+  } else {
+    T_h = sn[a.ix.utemp * sns]; // react_init: S_new is not touched, the heat release is evaluated at its temperature
+  }
+  double hi[N];
+  h_RT_fn(hi, T_h); // eos.RTY2Hi -> CKHMS (mechanism.H:2032-2041)
+  const double RT = PRX_RU * T_h;
+  double hr = 0.0;
+#pragma unroll
+  for (int n = 0; n < N; n++) {
+    const double irn = (rhoY[n] - so[(a.ix.ufs + n) * sos]) / dt - nr[(a.ix.ufs + n) * nrs];
+    ir[n * irs] = irn;
+    hr -= (hi[n] * (RT * prx_imw[n])) * irn;
+  }
+  ir[N * irs] = (eden_new - so[a.ix.ueden * sos]) / dt - nr[a.ix.ueden * nrs];
+  ir[(N + 1) * irs] = hr;
+  if (a.FC.p != nullptr) {
+    a.FC.p[cell_offset(c, a.len, a.FC.js, a.FC.ks)] = fc;
+  }
+}
+
 // ---- boundary loads / stores ---------------------------------------------------------
 // Array4: SoA, consecutive lanes <-> consecutive i: every component load is a coalesced
 // 256-byte warp transaction.  Flat (YCOrder): cell-major, used by the 1-D react() only.
@@ -162,6 +246,25 @@ __device__ __forceinline__ bool load_cell(
     y[N] = a.T.p[cell_offset(c, a.len, a.T.js, a.T.ks)];
     src.rhoe_init = a.rE.p[cell_offset(c, a.len, a.rE.js, a.rE.ks)];
     src.rhoesrc = a.rEsrc.p[cell_offset(c, a.len, a.rEsrc.js, a.rEsrc.ks)];
+  } else if (a.layout == LAYOUT_STATE) {
+    const double* so = a.sold.p + cell_offset(c, a.len, a.sold.js, a.sold.ks);
+    const double* nr = a.nonrs.p + cell_offset(c, a.len, a.nonrs.js, a.nonrs.ks);
+    double rho_old = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      y[k] = __ldg(so + (a.ix.ufs + k) * a.sold.ns);
+      src.rYsrc[k] = __ldg(nr + (a.ix.ufs + k) * a.nonrs.ns);
+      rho_old += y[k];
+    }
+    if (clean_init_massfrac) {
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        y[k] = fmin(fmax(0.0, y[k]), rho_old);
+      }
+    }
+    y[N] = so[a.ix.utemp * a.sold.ns];
+    src.rhoe_init = so[a.ix.ueint * a.sold.ns];
+    src.rhoesrc = state_rhoedot_ext(a, c);
   } else {
 #pragma unroll
     for (int k = 0; k < NEQ; k++) {
@@ -188,6 +291,49 @@ __device__ __forceinline__ void store_cell(
   const int reactor_type, const double fc, const int clean_init_massfrac, const bool resolve_T)
 {
   const double rhoe_out = src.rhoe_init + a.dt * src.rhoesrc;
+  if (a.layout == LAYOUT_STATE) {
+    // box_unflatten semantics on the reactor's side (rhoY out, T re-solved from (e_out, Y_out)), then React.cpp's unpack
+    double ynew[N];
+    double rho = 0.0;
+    const double* so = a.sold.p + cell_offset(c, a.len, a.sold.js, a.sold.ks);
+    if (clean_init_massfrac) {
+      double rho_old = 0.0, rho_oldclipped = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        rho_old += so[(a.ix.ufs + k) * a.sold.ns];
+      }
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        rho_oldclipped += fmin(fmax(0.0, so[(a.ix.ufs + k) * a.sold.ns]), rho_old);
+      }
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        const double yold = so[(a.ix.ufs + k) * a.sold.ns];
+        ynew[k] = yold + (y[k] - fmin(fmax(0.0, yold), rho_old)) * rho_old / rho_oldclipped;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        ynew[k] = y[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      rho += ynew[k];
+    }
+    double temp = y[N];
+    if (resolve_T) {
+      const double rho_inv = 1.0 / rho;
+      double Y[N];
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        Y[k] = ynew[k] * rho_inv;
+      }
+      t_from_energy(reactor_type, rhoe_out * rho_inv, Y, temp);
+    }
+    state_unpack(a, c, ynew, temp, src.rhoesrc, fc);
+    return;
+  }
   if (a.layout == LAYOUT_ARRAY4) {
     const long long o = cell_offset(c, a.len, a.rY.js, a.rY.ks);
     double ynew[N];
@@ -318,7 +464,11 @@ __device__ __forceinline__ double* bdf_vec(BdfCell& s, const int sel)
 
 // one cell per thread with the straight-line generated Jacobian only makes sense for small mechanisms (and the
 // 16k-line dodecane_lu Jacobian costs six minutes of compile time): large ones use the cooperative kernel
+#ifdef PRX_AUDIT_RK64_ONLY // audit build (-fmad=false, Makefile target `audit`): RK64 + probes only
+#define PRX_HAVE_BDF1 0
+#else
 #define PRX_HAVE_BDF1 (PRX_NUM_SPECIES <= 32)
+#endif
 #if PRX_HAVE_BDF1
 #ifndef PRX_OUTLINE
 #define PRX_OUTLINE 0 // bit 0: Jacobian out of line, bit 1: RHS out of line (separate register allocation, fewer spills in the loop)
@@ -524,7 +674,10 @@ struct SrcRef
 
 extern __shared__ double prx_dyn_smem[];
 
-#define PRX_HAVE_BDF2 (PRX_NUM_SPECIES <= 32) // one cell per thread stops making sense beyond that
+#ifndef PRX_FULL_VARIANTS
+#define PRX_FULL_VARIANTS 0 // 1: also build the measured dead ends (bdf2 / bdf3 / bdf4, profiles/README.md) for A/B runs
+#endif
+#define PRX_HAVE_BDF2 (PRX_FULL_VARIANTS && PRX_NUM_SPECIES <= 32) // one cell per thread stops making sense beyond that
 #if PRX_HAVE_BDF2
 
 template <bool A_SMEM>
@@ -1009,7 +1162,7 @@ struct SrcScal
   double rhoe_init, rhoesrc;
 };
 
-#define PRX_HAVE_BDF4 (PRX_NUM_SPECIES <= 12)
+#define PRX_HAVE_BDF4 (PRX_FULL_VARIANTS && PRX_NUM_SPECIES <= 12)
 #if PRX_HAVE_BDF4
 template <int NT>
 __global__ void __launch_bounds__(NT, 1) PRX_CAT(bdf4_kernel_, PRX_MECH_SUFFIX)(
@@ -1204,7 +1357,11 @@ cudaError_t launch_bdf4(const BoxArgs& a, const BdfParams& p, const SchedParams&
 // Same warp loop as above (refill / control / serve) with the GROUP as the unit: the 32/G cells of a warp
 // run their integrator coroutines (control flow replicated in the G lanes of a group, uniform inside it) and
 // meet at one converged place per request kind.  Blocks are single warps; no block barrier.
+#ifdef PRX_AUDIT_RK64_ONLY
+#define PRX_HAVE_COOP 0
+#else
 #define PRX_HAVE_COOP 1
+#endif
 #if PRX_HAVE_COOP
 // -DPRX_COOP_SERIAL_JAC: debugging aid - the analytic Jacobian evaluated by ONE lane with the generated
 // straight-line code instead of jac_coop (small mechanisms only)
@@ -1225,8 +1382,11 @@ __device__ __noinline__ void jac_serial(const int reactor_type, const double* __
 }
 #endif
 
-template <int G>
-__global__ void __launch_bounds__(32, PRX_COOP_MINBLOCKS) PRX_CAT(bdfc_kernel_, PRX_MECH_SUFFIX)(
+// W warps per block: W > 1 adds two block barriers per loop iteration (exit test, and in front of the RHS) that keep the SM's
+// warps in the same phase of the 630 KB kernel - ncu r02c on dodecane_lu: 31 % of the stall samples were "no instruction"
+// with independent single-warp blocks.
+template <int G, int W>
+__global__ void __launch_bounds__(32 * W, (PRX_COOP_MINBLOCKS / W) > 0 ? (PRX_COOP_MINBLOCKS / W) : 1) PRX_CAT(bdfc_kernel_, PRX_MECH_SUFFIX)(
   const BoxArgs a, const BdfParams p, const SchedParams sp, int* __restrict__ queue, DevStats* __restrict__ stats,
   double* __restrict__ jscratch, double* __restrict__ ascratch, const int cell_doubles)
 {
@@ -1235,10 +1395,12 @@ __global__ void __launch_bounds__(32, PRX_COOP_MINBLOCKS) PRX_CAT(bdfc_kernel_, 
   Cell s;
   const unsigned lane = threadIdx.x & 31u;
   const int grp = (int)lane / G;
+  const int wib = (int)(threadIdx.x >> 5);
   const Grp<G>& g = s.g;
-  s.base = prx_dyn_smem + (size_t)grp * cell_doubles;
-  s.gJ = jscratch + ((size_t)blockIdx.x * CPW + grp) * (NEQ * NEQ);
-  s.gA = (ascratch != nullptr) ? ascratch + ((size_t)blockIdx.x * CPW + grp) * (NEQ * NEQ) : nullptr;
+  const size_t slot = ((size_t)blockIdx.x * W + wib) * CPW + grp; // resident-cell slot of this group
+  s.base = prx_dyn_smem + ((size_t)wib * CPW + grp) * cell_doubles;
+  s.gJ = jscratch + slot * (NEQ * NEQ);
+  s.gA = (ascratch != nullptr) ? ascratch + slot * (NEQ * NEQ) : nullptr;
   s.nz = p.qmax + 1;
   int cell = -1;
   bool exhausted = false;
@@ -1322,14 +1484,22 @@ __global__ void __launch_bounds__(32, PRX_COOP_MINBLOCKS) PRX_CAT(bdfc_kernel_, 
         }
       }
     }
-    if (!__any_sync(FULL, !(exhausted && (cell < 0)))) {
+    if (W > 1) {
+      if (!__syncthreads_or(!(exhausted && (cell < 0)))) {
+        break;
+      }
+    } else if (!__any_sync(FULL, !(exhausted && (cell < 0)))) {
       break;
     }
     // ---- (2) control ----
     if (cell >= 0 && req == REQ_NONE) {
       req = bdf_resume(s, pc);
     }
-    __syncwarp();
+    if (W > 1) {
+      __syncthreads(); // phase barrier: the block's warps enter the RHS / Jacobian / LU service together
+    } else {
+      __syncwarp();
+    }
     // ---- (3) serve ----
     const unsigned m_rhs = __ballot_sync(FULL, req == REQ_RHS);
     const unsigned m_jac = __ballot_sync(FULL, req == REQ_JAC);
@@ -1445,15 +1615,15 @@ __global__ void __launch_bounds__(32, PRX_COOP_MINBLOCKS) PRX_CAT(bdfc_kernel_, 
   flush_stats(ls, stats);
 }
 
-template <int G>
-cudaError_t launch_bdfc(const BoxArgs& a, const BdfParams& p, const SchedParams& sp, int* queue, DevStats* stats, cudaStream_t stream)
+template <int G, int W>
+cudaError_t launch_bdfc_w(const BoxArgs& a, const BdfParams& p, const SchedParams& sp, int* queue, DevStats* stats, cudaStream_t stream)
 {
-  auto kern = PRX_CAT(bdfc_kernel_, PRX_MECH_SUFFIX)<G>;
+  auto kern = PRX_CAT(bdfc_kernel_, PRX_MECH_SUFFIX)<G, W>;
   constexpr int CPW = 32 / G;
   // Newton matrix in the shared-memory block unless it is large (PRX_COOP_A_GLOBAL: 0 never, 1 always, else > 8 KB)
   const bool a_global = (sp.coop_a_global == 1) || (sp.coop_a_global != 0 && sizeof(double) * NEQ * NEQ > 8192);
   const int cell_doubles = BdfStoreCoop<G>::doubles_per_cell(p.qmax, a_global);
-  const size_t smem = sizeof(double) * (size_t)CPW * cell_doubles;
+  const size_t smem = sizeof(double) * (size_t)W * CPW * cell_doubles;
   int dev = 0, sms = 148, per_sm = 0, max_optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1466,28 +1636,45 @@ cudaError_t launch_bdfc(const BoxArgs& a, const BdfParams& p, const SchedParams&
     return e;
   }
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem) != cudaSuccess || per_sm < 1) {
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * W, smem) != cudaSuccess || per_sm < 1) {
     return cudaErrorInvalidConfiguration;
   }
-  if (sp.max_warps_per_sm > 0 && per_sm > sp.max_warps_per_sm) {
-    per_sm = sp.max_warps_per_sm;
+  if (sp.max_warps_per_sm > 0 && per_sm * W > sp.max_warps_per_sm) {
+    per_sm = sp.max_warps_per_sm / W > 0 ? sp.max_warps_per_sm / W : 1;
   }
   long long grid = (long long)sms * per_sm; // persistent: one full wave, a multiple of the SM count
-  const long long needed = ((long long)a.ncells + CPW - 1) / CPW;
+  const long long needed = ((long long)a.ncells + CPW * W - 1) / (CPW * W);
   grid = needed < grid ? needed : grid;
   double* jscratch = nullptr; // savedJ slots, one per resident cell (stream-ordered, pool-backed after the first call)
-  e = cudaMallocAsync(&jscratch, sizeof(double) * (size_t)grid * CPW * NEQ * NEQ * (a_global ? 2 : 1), stream);
+  const size_t slots = (size_t)grid * W * CPW;
+  e = cudaMallocAsync(&jscratch, sizeof(double) * slots * NEQ * NEQ * (a_global ? 2 : 1), stream);
   if (e != cudaSuccess) {
     return e;
   }
-  double* ascratch = a_global ? jscratch + (size_t)grid * CPW * NEQ * NEQ : nullptr;
+  double* ascratch = a_global ? jscratch + slots * NEQ * NEQ : nullptr;
   e = cudaMemsetAsync(queue, 0, sizeof(int), stream);
   if (e == cudaSuccess) {
-    kern<<<(int)grid, 32, smem, stream>>>(a, p, sp, queue, stats, jscratch, ascratch, cell_doubles);
+    kern<<<(int)grid, 32 * W, smem, stream>>>(a, p, sp, queue, stats, jscratch, ascratch, cell_doubles);
     e = cudaGetLastError();
   }
   const cudaError_t e2 = cudaFreeAsync(jscratch, stream);
   return e != cudaSuccess ? e : e2;
+}
+
+#ifndef PRX_COOP_BLOCK_WARPS
+#define PRX_COOP_BLOCK_WARPS 1 // default warps per block of the cooperative kernel (PRX_BLOCK_WARPS overrides: 1 or 4)
+#endif
+template <int G>
+cudaError_t launch_bdfc(const BoxArgs& a, const BdfParams& p, const SchedParams& sp, int* queue, DevStats* stats, cudaStream_t stream)
+{
+  const int w = sp.block_warps > 0 ? sp.block_warps : PRX_COOP_BLOCK_WARPS;
+  if (w >= 8 && G == 32) { // (W > 1 is built for the one-warp-per-cell layout only: compile time)
+    return launch_bdfc_w<(G == 32 ? G : 32), 8>(a, p, sp, queue, stats, stream);
+  }
+  if (w >= 4 && G == 32) {
+    return launch_bdfc_w<(G == 32 ? G : 32), 4>(a, p, sp, queue, stats, stream);
+  }
+  return launch_bdfc_w<G, 1>(a, p, sp, queue, stats, stream);
 }
 #endif // PRX_HAVE_COOP
 
@@ -1598,6 +1785,57 @@ __global__ void PRX_CAT(unflatten_kernel_, PRX_MECH_SUFFIX)(
   store_cell(a, c, y, src, reactor_type, (double)fcunt[c], clean_init_massfrac, true);
 }
 
+// ---- unfused react_state pack / unpack (for integrator kernels whose load/store phase is not fused: cooperative kernel) ----
+__global__ void PRX_CAT(state_pack_kernel_, PRX_MECH_SUFFIX)(const BoxArgs a)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.ncells) {
+    return;
+  }
+  const double* so = a.sold.p + cell_offset(c, a.len, a.sold.js, a.sold.ks);
+  const long long o = cell_offset(c, a.len, a.rY.js, a.rY.ks);
+  for (int k = 0; k < N; k++) {
+    a.rY.p[o + k * a.rY.ns] = so[(a.ix.ufs + k) * a.sold.ns];
+  }
+  a.T.p[cell_offset(c, a.len, a.T.js, a.T.ks)] = so[a.ix.utemp * a.sold.ns];
+  a.rE.p[cell_offset(c, a.len, a.rE.js, a.rE.ks)] = so[a.ix.ueint * a.sold.ns];
+  a.rEsrc.p[cell_offset(c, a.len, a.rEsrc.js, a.rEsrc.ks)] = state_rhoedot_ext(a, c);
+}
+
+__global__ void PRX_CAT(state_unpack_kernel_, PRX_MECH_SUFFIX)(const BoxArgs a)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.ncells) {
+    return;
+  }
+  double rhoY[N];
+  const long long o = cell_offset(c, a.len, a.rY.js, a.rY.ks);
+  for (int k = 0; k < N; k++) {
+    rhoY[k] = a.rY.p[o + k * a.rY.ns];
+  }
+  state_unpack(
+    a, c, rhoY, a.T.p[cell_offset(c, a.len, a.T.js, a.T.ks)], a.rEsrc.p[cell_offset(c, a.len, a.rEsrc.js, a.rEsrc.ks)],
+    a.FC.p[cell_offset(c, a.len, a.FC.js, a.FC.ks)]);
+}
+
+cudaError_t launch_state_pack(const BoxArgs& a, cudaStream_t stream)
+{
+  if (a.ncells <= 0) {
+    return cudaSuccess;
+  }
+  PRX_CAT(state_pack_kernel_, PRX_MECH_SUFFIX)<<<(a.ncells + 127) / 128, 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_state_unpack(const BoxArgs& a, const prx_config&, cudaStream_t stream)
+{
+  if (a.ncells <= 0) {
+    return cudaSuccess;
+  }
+  PRX_CAT(state_unpack_kernel_, PRX_MECH_SUFFIX)<<<(a.ncells + 127) / 128, 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_flatten(
   const BoxArgs& a, const prx_config& cfg, int ordering, double* y, double* ysrc, double* e, double* esrc, cudaStream_t stream)
 {
@@ -1650,7 +1888,7 @@ cudaError_t launch_rk64(const BoxArgs& a, const prx_config& cfg, int* queue, Dev
   p.nsub_guess = cfg.rk64_nsubsteps_guess;
   p.nsub_min = cfg.rk64_nsubsteps_min;
   p.nsub_max = cfg.rk64_nsubsteps_max;
-  p.array4_semantics = (a.layout == LAYOUT_ARRAY4);
+  p.array4_semantics = (a.layout != LAYOUT_FLAT);
   auto kern = PRX_CAT(rk64_kernel_, PRX_MECH_SUFFIX);
   const int grid = persistent_grid((const void*)kern, a.ncells, PRX_RK_BLOCK);
   cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(int), stream);
@@ -1683,7 +1921,7 @@ cudaError_t launch_bdf(
   p.maxnef = 100;
   p.msbj = 100;
   p.clean_init_massfrac = cfg.clean_init_massfrac;
-  p.array4_semantics = (a.layout == LAYOUT_ARRAY4);
+  p.array4_semantics = (a.layout != LAYOUT_FLAT);
   // kernel generation: 1 = shared-memory columns incl. the Newton matrix, 2 = columns, matrix thread-local,
   // 0 = first generation (thread-local state, straight-line chemistry); default per mechanism
   const int variant = effective_bdf_variant(sp);
@@ -1735,8 +1973,14 @@ cudaError_t launch_bdf(
   }
   kern<<<grid, PRX_BLOCK, 0, stream>>>(a, p, sp, queue, stats);
   return cudaGetLastError();
-#else
+#elif PRX_HAVE_COOP
   return launch_bdfc<32>(a, p, sp, queue, stats, stream);
+#else
+  (void)queue;
+  (void)stats;
+  (void)stream;
+  (void)p;
+  return cudaErrorNotSupported; // audit build: no BDF kernels
 #endif
 }
 
@@ -1816,8 +2060,10 @@ cudaError_t probe_jac(int n, int reactor_type, const double* y, double* J, cudaS
   return e;
 }
 
+int bdf_is_fused(const SchedParams& sp) { return effective_bdf_variant(sp) == 0; }
+
 const MechOps g_ops = {PRX_NUM_SPECIES, PRX_NUM_REACTIONS, PRX_MECH_NAME, prx_species_names, launch_rk64, launch_bdf, kernel_name, probe_rhs, probe_jac,
-                       launch_flatten, launch_unflatten};
+                       launch_flatten, launch_unflatten, launch_state_pack, launch_state_unpack, bdf_is_fused};
 
 } // namespace
 

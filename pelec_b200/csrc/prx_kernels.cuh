@@ -22,7 +22,15 @@ struct ArrViewI
   long long js, ks, ns;
 };
 
-enum Layout { LAYOUT_ARRAY4 = 0, LAYOUT_FLAT = 1 };
+// LAYOUT_STATE: the fused PeleC::react_state body (PC/Source/React.cpp:181-343): the kernel reads S_old / S_new /
+// non_react_src itself (pack), integrates, and writes S_new and I_R (unpack + heat release) - no STemp / extsrc copies.
+enum Layout { LAYOUT_ARRAY4 = 0, LAYOUT_FLAT = 1, LAYOUT_STATE = 2 };
+
+// PeleC state-vector component indices (PC/Source/IndexDefines.H)
+struct StateIx
+{
+  int urho, umx, umy, umz, ueden, ueint, utemp, ufs;
+};
 
 struct BoxArgs
 {
@@ -38,6 +46,10 @@ struct BoxArgs
   double* e;
   const double* esrc;
   double* fc;
+  // state layout (fused react_state): S_old, S_new (in/out), non-reacting sources, I_R (N+2 components out); FC optional
+  ArrView sold, snew, nonrs, IR;
+  StateIx ix;
+  int do_update; // !react_init
   double dt, time;
   const int* order; // optional: queue position -> cell index (cells sorted by temperature), nullptr = identity
 };
@@ -89,6 +101,11 @@ struct MechOps
   cudaError_t (*unflatten)(
     const BoxArgs&, const prx_config&, int ordering, const double* y, const double* e, const long long* fcunt,
     cudaStream_t stream);
+  // unfused form of the react_state body for integrator kernels without a fused load/store phase (cooperative kernel):
+  // pack fills the Array4 views of the same BoxArgs (rY, T, rE, rEsrc scratch; rYsrc aliases nonrs), unpack consumes them
+  cudaError_t (*state_pack)(const BoxArgs&, cudaStream_t stream);
+  cudaError_t (*state_unpack)(const BoxArgs&, const prx_config&, cudaStream_t stream);
+  int (*bdf_is_fused)(const SchedParams&); // 1: launch_bdf handles LAYOUT_STATE itself
 };
 
 const MechOps* mech_ops_LiDryer();

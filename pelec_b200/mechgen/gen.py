@@ -69,6 +69,7 @@ class Emitter:
         self.fl = flavour
         self.N = len(d["species"])
         self.L = []
+        self.exp2 = os.environ.get("PRX_GEN_EXP2", "1") != "0"
         self.q = "PRX_DEVFN " if flavour == "cuda" else "static inline "
 
     def w(self, s=""):
@@ -161,6 +162,17 @@ class Emitter:
         return "%s * exp(-(%s) * invT)" % (lit(A), Ea)
 
     @staticmethod
+    def arrh_parts(A, beta, Ea):
+        """(A literal, argument of the exponential or None): the pieces of arrh()."""
+        if beta is None and Ea is None:
+            return lit(A), None
+        if beta is not None and Ea is not None:
+            return lit(A), "(%s) * logT - (%s) * invT" % (beta, Ea)
+        if beta is not None:
+            return lit(A), "(%s) * logT" % beta
+        return lit(A), "-(%s) * invT" % Ea
+
+    @staticmethod
     def conc_product(idx, var="sc"):
         return " * ".join("%s[%d]" % (var, i) for i in idx)
 
@@ -244,7 +256,17 @@ class Emitter:
         w("  (void)refC; (void)refCinv; (void)mixture;")
         for r in d["reactions"]:
             w("  { // R%d: %s" % (r["idx"], r["eq"]))
-            w("    const double k_f = %s;" % self.arrh(r["A"], r["beta"], r["Ea"]))
+            # device flavour: the two independent exponentials of a reversible reaction (rate constant, equilibrium constant)
+            # go through ONE call that evaluates both chains interleaved (PRX_EXP2, prx_chem.cuh): same arguments, same
+            # per-value arithmetic, half the dependent-latency exposure (ncu r02c: a single out-of-line exp is a chain of
+            # 13 dependent DFMAs and the warp waits for its latency, not for issue slots)
+            A_l, k_arg = self.arrh_parts(r["A"], r["beta"], r["Ea"])
+            paired = (self.fl == "cuda" and self.exp2 and k_arg is not None and r["reversible"] and r["type"] != "falloff")
+            if paired:
+                w("    const prx_d2 ee = PRX_EXP2(%s, -(%s));" % (k_arg, self.dg_sum(r["dG"], "g_RT")))
+                w("    const double k_f = %s * ee.x;" % A_l)
+            else:
+                w("    const double k_f = %s;" % self.arrh(r["A"], r["beta"], r["Ea"]))
             pre = ""
             if r["type"] in ("three_body", "falloff"):
                 w("    double Corr = %s;" % self.corr_expr(r["eff"]))
@@ -266,8 +288,8 @@ class Emitter:
             if r["reversible"]:
                 rc = self.refc_factor(r["refC"])
                 rcs = "" if rc is None else ("%s * " % (rc if rc.startswith("(") else "(" + rc + ")"))
-                w("    const double qr = %sk_f * exp(-(%s)) * %s(%s);" % (
-                    pre, self.dg_sum(r["dG"], "g_RT"), rcs, self.conc_product(r["products"])))
+                kc = "ee.y" if paired else "exp(-(%s))" % self.dg_sum(r["dG"], "g_RT")
+                w("    const double qr = %sk_f * %s * %s(%s);" % (pre, kc, rcs, self.conc_product(r["products"])))
             else:
                 w("    const double qr = 0.0;")
             w("    const double qdot = qf - qr;")
@@ -843,8 +865,11 @@ def generate_all(repo_root, mechs=("LiDryer", "drm19", "dodecane_lu")):
         out.append(p)
         p = os.path.join(repo_root, "pelec_b200", "csrc", "gen", "mech_%s.cuh" % m)
         text = emit(m, "cuda")
-        # dodecane_lu's mechanism tables already fill the 64 KB constant bank: its straight-line code keeps inline literals
-        if os.environ.get("PRX_GEN_CONSTIFY", "1") != "0" and len(load(m)["species"]) <= 32:
+        # Literal pool: OFF by default.  Measured on B200 (profiles/README.md, session r02d): 21 % fewer executed instructions
+        # but 12 % SLOWER BDF (75.1 vs 66.7 ms per 128^3: the LDC'd literals live in registers, 460 B more spills per thread)
+        # and 2 % slower RK64 - the chemistry is bound by dependent FP64 chains, and the UMOV pairs it removes were filling
+        # issue slots that are otherwise idle.  (dodecane_lu's mechanism tables fill the 64 KB constant bank anyway.)
+        if os.environ.get("PRX_GEN_CONSTIFY", "0") == "1" and len(load(m)["species"]) <= 32:
             text = constify(text)
         write_if_changed(p, text)
         out.append(p)
@@ -872,7 +897,7 @@ def _function_bodies(text):
 def _count(body):
     import re
     body = re.sub(r"//.*", "", body)
-    trans = len(re.findall(r"\b(?:exp|log10|log)\(", body))
+    trans = len(re.findall(r"\b(?:exp|log10|log)\(", body)) + 2 * len(re.findall(r"\bPRX_EXP2\(", body))
     # binary arithmetic operators (unary signs of literals are not operations)
     arith = len(re.findall(r"(?<=[\w\)\]]) [-+*/] (?=[\w\(\-])", body)) + len(re.findall(r"[-+*/]=", body))
     return arith, trans

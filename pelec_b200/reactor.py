@@ -50,6 +50,10 @@ class prx_array4(C.Structure):
                 ("nstride", C.c_longlong), ("begin", C.c_int * 3), ("end", C.c_int * 3), ("ncomp", C.c_int)]
 
 
+class prx_state_index(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("urho", "umx", "umy", "umz", "ueden", "ueint", "utemp", "ufs", "nvar")]
+
+
 class prx_stats(C.Structure):
     _fields_ = [(n, C.c_longlong) for n in
                 ("cells", "cells_masked", "n_steps", "n_rhs", "n_jac", "n_setups", "n_newton", "n_errfail",
@@ -83,6 +87,10 @@ def load_library():
     L.prx_default_config.argtypes = [C.POINTER(prx_config)]
     L.prx_react_box.argtypes = [vp, ip, ip, a4, a4, a4, a4, a4, a4, a4, C.c_double, C.c_double, vp]
     L.prx_react_flat.argtypes = [vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, vp]
+    L.prx_react_boxes.argtypes = [vp, C.c_int, ip, ip, a4, a4, a4, a4, a4, a4, a4, C.c_double, C.c_double, vp]
+    sx = C.POINTER(prx_state_index)
+    L.prx_react_state_box.argtypes = [vp, ip, ip, a4, a4, a4, a4, a4, sx, C.c_double, C.c_int, vp]
+    L.prx_react_state_boxes.argtypes = [vp, C.c_int, ip, ip, a4, a4, a4, a4, a4, sx, C.c_double, C.c_int, vp]
     L.prx_flatten.argtypes = [vp, ip, ip, C.c_int, C.c_int, a4, a4, a4, a4, a4, vp, vp, vp, vp, vp]
     L.prx_unflatten.argtypes = [vp, ip, ip, C.c_int, C.c_int, a4, a4, a4, a4, a4, vp, vp, vp, C.c_double, vp]
     L.prx_react_flat_host.argtypes = [vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int]
@@ -126,7 +134,7 @@ class Array4:
     def __init__(self, tensor, begin=(0, 0, 0)):
         if tensor.dim() == 3:
             tensor = tensor.unsqueeze(0)
-        assert tensor.dim() == 4 and tensor.is_contiguous() or tensor.dim() == 4
+        assert tensor.dim() == 4 and tensor.stride(3) == 1, "Array4 needs a [ncomp, nz, ny, nx] tensor with unit stride in i"
         self.t = tensor
         self.begin = tuple(int(b) for b in begin)
 
@@ -238,6 +246,51 @@ class ReactorB200:
         self._check(self.lib.prx_react_box(
             self.h, lo, hi, *[C.byref(s) for s in structs], C.byref(m) if m is not None else None,
             float(dt_react), float(time), sp))
+        return 0
+
+    # -- several boxes in one call (the caller's MFIter loop) ------------------------------------
+    def react_boxes(self, boxes, rY, rYsrc, T, rE, rEsrc, FC, masks, dt_react, time, stream=None):
+        """boxes: list of Box; every array argument: list of Array4, one per box (masks may be None)."""
+        nb = len(boxes)
+        lo = (C.c_int * (3 * nb))(*[v for b in boxes for v in b.lo])
+        hi = (C.c_int * (3 * nb))(*[v for b in boxes for v in b.hi])
+        arrs = [(prx_array4 * nb)(*[a.c_struct() for a in lst]) for lst in (rY, rYsrc, T, rE, rEsrc, FC)]
+        m = (prx_array4 * nb)(*[a.c_struct() for a in masks]) if masks is not None else None
+        sp = C.c_void_p(stream) if stream else None
+        self._check(self.lib.prx_react_boxes(self.h, nb, lo, hi, *arrs, m, float(dt_react), float(time), sp))
+        return 0
+
+    # -- fused PeleC::react_state body (PC/Source/React.cpp:140-343) ----------------------------
+    @staticmethod
+    def state_index(nspec, urho=0, umx=1, umy=2, umz=3, ueden=4, ueint=5, utemp=6, ufs=7, nvar=None):
+        """PC/Source/IndexDefines.H:3-12 (NUM_ADV = NUM_AUX = 0: UFS = 7, NVAR = 7 + NUM_SPECIES)"""
+        ix = prx_state_index()
+        ix.urho, ix.umx, ix.umy, ix.umz, ix.ueden, ix.ueint, ix.utemp, ix.ufs = urho, umx, umy, umz, ueden, ueint, utemp, ufs
+        ix.nvar = ufs + nspec if nvar is None else nvar
+        return ix
+
+    def react_state(self, box, sold, snew, nonrs, I_R, dt, do_update=True, work=None, ix=None, stream=None):
+        lo = (C.c_int * 3)(*box.lo)
+        hi = (C.c_int * 3)(*box.hi)
+        structs = [a.c_struct() for a in (sold, snew, nonrs, I_R)]
+        w = work.c_struct() if work is not None else None
+        ix = ix or self.state_index(self.N)
+        sp = C.c_void_p(stream) if stream else None
+        self._check(self.lib.prx_react_state_box(
+            self.h, lo, hi, *[C.byref(x) for x in structs], C.byref(w) if w is not None else None, C.byref(ix),
+            float(dt), int(bool(do_update)), sp))
+        return 0
+
+    def react_state_boxes(self, boxes, sold, snew, nonrs, I_R, dt, do_update=True, work=None, ix=None, stream=None):
+        nb = len(boxes)
+        lo = (C.c_int * (3 * nb))(*[v for b in boxes for v in b.lo])
+        hi = (C.c_int * (3 * nb))(*[v for b in boxes for v in b.hi])
+        arrs = [(prx_array4 * nb)(*[a.c_struct() for a in lst]) for lst in (sold, snew, nonrs, I_R)]
+        w = (prx_array4 * nb)(*[a.c_struct() for a in work]) if work is not None else None
+        ix = ix or self.state_index(self.N)
+        sp = C.c_void_p(stream) if stream else None
+        self._check(self.lib.prx_react_state_boxes(self.h, nb, lo, hi, *arrs, w, C.byref(ix), float(dt),
+                                                   int(bool(do_update)), sp))
         return 0
 
     # -- flat react on device tensors ----------------------------------------------------------
