@@ -174,6 +174,14 @@ PRX_API int prx_react_state_boxes(
   const prx_array4* nonrs, const prx_array4* I_R, const prx_array4* work, const prx_state_index* ix, double dt,
   int do_update, void* cuda_stream);
 
+/* ---- PeleC::computeTemp's pointwise kernel (PC/Source/PeleC.cpp:2254-2272 -> pc_cmpTemp, PC/Source/Utilities.H:70-84) ----
+ * state(UTEMP) <- REY2T(rho, rho*e_int / rho, rhoY / rho, guess = state(UTEMP)), in place, for every cell of every box; all
+ * boxes on cuda_stream.  EOS only (no reactor state is used); reset_internal_energy stays with the caller.  SURVEY.md 8f-3. */
+PRX_API int prx_compute_temp_boxes(
+  prx_handle* h, int nboxes, const int* lo, const int* hi, const prx_array4* state, const prx_state_index* ix,
+  void* cuda_stream);
+
+
 /* ---- ReactorBase::react, flat version (ReactorBase.H:42-54), DEVICE pointers ----
  * y [ncells*(N+1)] YCOrder (cell-major, T last), ysrc [ncells*N], e [ncells], esrc [ncells].
  * Reference semantics of the 1-D call: T is taken from y (no initial REY2T) and the

@@ -670,6 +670,47 @@ int prx_react_state_box(
   return react_state_one(h, lo, hi, sold, snew, nonrs, I_R, work, ix, dt, do_update, (cudaStream_t)cuda_stream);
 }
 
+// ---- PeleC::computeTemp's kernel (PC/Source/PeleC.cpp:2254-2272 -> pc_cmpTemp, Utilities.H:70-84) -----------------------
+int prx_compute_temp_boxes(
+  prx_handle* h, int nboxes, const int* lo, const int* hi, const prx_array4* state, const prx_state_index* ix, void* cuda_stream)
+{
+  if (h == nullptr || nboxes < 0 || ix == nullptr || (nboxes > 0 && (!lo || !hi || !state))) {
+    return PRX_ERR_BAD_ARG;
+  }
+  const int N = h->ops->num_species;
+  if (ix->nvar < ix->ufs + N) {
+    return fail(h, PRX_ERR_BAD_ARG, "prx_compute_temp_boxes: state index table does not fit NUM_SPECIES");
+  }
+  DeviceGuard g(h->device);
+  NvtxRange nvtx("prx::computeTemp");
+  for (int b = 0; b < nboxes; b++) {
+    BoxArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.layout = LAYOUT_STATE;
+    long long nc = 1;
+    for (int d = 0; d < 3; d++) {
+      a.len[d] = hi[3 * b + d] - lo[3 * b + d] + 1;
+      nc *= a.len[d] > 0 ? a.len[d] : 0;
+    }
+    if (nc == 0) {
+      continue;
+    }
+    if (nc > 2147483647LL || !view_of(state + b, lo + 3 * b, ix->nvar, &a.snew, hi + 3 * b)) {
+      return fail(h, PRX_ERR_BAD_ARG, "prx_compute_temp_boxes: null/short Array4 or box outside the array");
+    }
+    a.ncells = (int)nc;
+    a.ix.urho = ix->urho;
+    a.ix.ueint = ix->ueint;
+    a.ix.utemp = ix->utemp;
+    a.ix.ufs = ix->ufs;
+    const cudaError_t e = h->ops->compute_temp(a, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) {
+      return fail(h, PRX_ERR_CUDA, "compute_temp", e);
+    }
+  }
+  return PRX_OK;
+}
+
 // ---- multi-box entry points: the MFIter loop of the caller (PC/Source/React.cpp:133-138) in one call ------------------
 // PeleC hands the reactor 16^3 - 64^3 boxes; a single small box cannot fill 148 SMs and its latency is the critical path of
 // its slowest cell.  The boxes of one call are independent, so they are issued round-robin on internal streams (as AMReX does

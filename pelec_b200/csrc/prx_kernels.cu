@@ -1818,6 +1818,43 @@ __global__ void PRX_CAT(state_unpack_kernel_, PRX_MECH_SUFFIX)(const BoxArgs a)
     a.FC.p[cell_offset(c, a.len, a.FC.js, a.FC.ks)]);
 }
 
+// ---- PeleC::computeTemp's pointwise kernel pc_cmpTemp (PC/Source/Utilities.H:70-84): T <- REY2T(rho, e, Y) in
+// place on a state FAB.  One thread per cell, every component read is a coalesced 256-byte warp transaction along i; the
+// kernel is HBM-bound ((N + 3) doubles in, 1 out per cell).  (reset_internal_energy, the dual-energy bookkeeping PeleC runs
+// first, stays with the caller.)
+__global__ void PRX_CAT(compute_temp_kernel_, PRX_MECH_SUFFIX)(const BoxArgs a)
+{
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < a.ncells; c += gridDim.x * blockDim.x) {
+    double* S = a.snew.p + cell_offset(c, a.len, a.snew.js, a.snew.ks);
+    const long long ns = a.snew.ns;
+    const double rho = S[a.ix.urho * ns];
+    const double rhoInv = 1.0 / rho;
+    double T = S[a.ix.utemp * ns];
+    const double e = S[a.ix.ueint * ns] * rhoInv;
+    double Y[N];
+#pragma unroll
+    for (int n = 0; n < N; n++) {
+      Y[n] = __ldg(S + (a.ix.ufs + n) * ns) * rhoInv;
+    }
+    t_from_energy<1>(e, Y, T);
+    S[a.ix.utemp * ns] = T;
+  }
+}
+
+cudaError_t launch_compute_temp(const BoxArgs& a, cudaStream_t stream)
+{
+  if (a.ncells <= 0) {
+    return cudaSuccess;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long want = ((long long)a.ncells + 255) / 256;
+  const long long cap = (long long)sms * 8; // a multiple of the SM count; grid-stride beyond it
+  PRX_CAT(compute_temp_kernel_, PRX_MECH_SUFFIX)<<<(int)(want < cap ? want : cap), 256, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_state_pack(const BoxArgs& a, cudaStream_t stream)
 {
   if (a.ncells <= 0) {
@@ -2063,7 +2100,7 @@ cudaError_t probe_jac(int n, int reactor_type, const double* y, double* J, cudaS
 int bdf_is_fused(const SchedParams& sp) { return effective_bdf_variant(sp) == 0; }
 
 const MechOps g_ops = {PRX_NUM_SPECIES, PRX_NUM_REACTIONS, PRX_MECH_NAME, prx_species_names, launch_rk64, launch_bdf, kernel_name, probe_rhs, probe_jac,
-                       launch_flatten, launch_unflatten, launch_state_pack, launch_state_unpack, bdf_is_fused};
+                       launch_flatten, launch_unflatten, launch_state_pack, launch_state_unpack, bdf_is_fused, launch_compute_temp};
 
 } // namespace
 

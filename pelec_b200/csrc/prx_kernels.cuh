@@ -106,6 +106,7 @@ struct MechOps
   cudaError_t (*state_pack)(const BoxArgs&, cudaStream_t stream);
   cudaError_t (*state_unpack)(const BoxArgs&, const prx_config&, cudaStream_t stream);
   int (*bdf_is_fused)(const SchedParams&); // 1: launch_bdf handles LAYOUT_STATE itself
+  cudaError_t (*compute_temp)(const BoxArgs&, cudaStream_t stream); // pc_cmpTemp on a.snew
 };
 
 const MechOps* mech_ops_LiDryer();

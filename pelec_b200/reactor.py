@@ -91,6 +91,7 @@ def load_library():
     sx = C.POINTER(prx_state_index)
     L.prx_react_state_box.argtypes = [vp, ip, ip, a4, a4, a4, a4, a4, sx, C.c_double, C.c_int, vp]
     L.prx_react_state_boxes.argtypes = [vp, C.c_int, ip, ip, a4, a4, a4, a4, a4, sx, C.c_double, C.c_int, vp]
+    L.prx_compute_temp_boxes.argtypes = [vp, C.c_int, ip, ip, a4, sx, vp]
     L.prx_flatten.argtypes = [vp, ip, ip, C.c_int, C.c_int, a4, a4, a4, a4, a4, vp, vp, vp, vp, vp]
     L.prx_unflatten.argtypes = [vp, ip, ip, C.c_int, C.c_int, a4, a4, a4, a4, a4, vp, vp, vp, C.c_double, vp]
     L.prx_react_flat_host.argtypes = [vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int]
@@ -291,6 +292,17 @@ class ReactorB200:
         sp = C.c_void_p(stream) if stream else None
         self._check(self.lib.prx_react_state_boxes(self.h, nb, lo, hi, *arrs, w, C.byref(ix), float(dt),
                                                    int(bool(do_update)), sp))
+        return 0
+
+    # -- PeleC::computeTemp's kernel (pc_cmpTemp) -------------------------------------------------
+    def compute_temp(self, boxes, states, ix=None, stream=None):
+        nb = len(boxes)
+        lo = (C.c_int * (3 * nb))(*[v for b in boxes for v in b.lo])
+        hi = (C.c_int * (3 * nb))(*[v for b in boxes for v in b.hi])
+        arr = (prx_array4 * nb)(*[a.c_struct() for a in states])
+        ix = ix or self.state_index(self.N)
+        sp = C.c_void_p(stream) if stream else None
+        self._check(self.lib.prx_compute_temp_boxes(self.h, nb, lo, hi, arr, C.byref(ix), sp))
         return 0
 
     # -- flat react on device tensors ----------------------------------------------------------

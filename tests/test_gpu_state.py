@@ -229,3 +229,32 @@ def test_react_state_boxes_equals_box_by_box():
         for x, y in zip(a, m):
             assert torch.equal(x, y)
     r.close()
+
+
+@pytest.mark.parametrize("mech", ["LiDryer", "drm19", "dodecane_lu"])
+def test_compute_temp_matches_oracle_rey2t(mech):
+    """pc_cmpTemp (PC/Source/Utilities.H:70-84): T <- REY2T(rho, e, Y) in place, on a ragged box inside a padded, offset FAB."""
+    orc = Oracle(mech)
+    dev = torch.device("cuda:0")
+    shape, pad, begin = (37, 5, 3), (1, 2, 0), (4, -3, 0)
+    sold, _, _ = make_state(orc, shape, 3)
+    rng = np.random.default_rng(5)
+    sold[6] += rng.uniform(-150, 150, sold.shape[1])  # a poor guess
+    t = to_fab(sold, shape, dev, pad, fill=-1.0)
+    t0 = t.clone()
+    r = ReactorB200.create("ReactorRK64", mech)
+    r.init(1, 1)
+    lo = (begin[0] + pad[0], begin[1] + pad[1], begin[2] + pad[2])
+    hi = (lo[0] + shape[0] - 1, lo[1] + shape[1] - 1, lo[2] + shape[2] - 1)
+    r.compute_temp([Box(lo, hi)], [Array4(t, begin)])
+    torch.cuda.synchronize()
+    got = from_fab(t, shape, pad)
+    Y = (sold[7:] / sold[0]).T.copy()
+    ref = orc.ey2t(sold[5] / sold[0], Y, sold[6])
+    assert (np.abs(got[6] - ref) / ref).max() < 1e-12
+    got[6] = sold[6]
+    assert np.array_equal(got, sold)  # nothing but UTEMP changes
+    inside = torch.zeros(t.shape[1:], dtype=torch.bool, device=dev)
+    inside[pad[2]:pad[2] + shape[2], pad[1]:pad[1] + shape[1], pad[0]:pad[0] + shape[0]] = True
+    assert torch.equal(t[:, ~inside], t0[:, ~inside])
+    r.close()

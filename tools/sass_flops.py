@@ -8,7 +8,7 @@ import csv, gzip, io, json, sys
 
 def raw(path):
     rows = list(csv.reader(io.StringIO(gzip.open(path, "rt").read())))
-    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
     return {a: (str(float(c.replace(",", "")) * scale[u]) if u in scale else c) for a, u, c in zip(rows[0], rows[1], rows[2])}
 
 
