@@ -66,12 +66,22 @@ def workload_name(a):
     return "%d^3 synthetic %s states (%s), %s, dt=%g s, %s" % (a.n, a.mech, src, a.reactor, a.dt, tol)
 
 
+def config_of(a):
+    """The `config` object of the JSON line: identical for the b200 and the reference arm (same workload)."""
+    from pelec_b200.mechgen import gen
+    N, n = gen.op_counts(a.mech)["N"], a.n
+    return {"workload": workload_name(a), "mechanism": a.mech, "reactor": a.reactor,
+            "cells_per_gpu_per_step": n ** 3, "sharding": "one %d^3 box per GPU, no data-path collective" % n,
+            "l2": "each step reads/writes a fresh %.0f MB copy of the state (> 126 MB L2)" % ((2 * N + 6) * 8 * n ** 3 / 1e6)}
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU legs (reference / oracle port)
 # ------------------------------------------------------------------------------------------------
 def _cpu_worker(args):
     """One process = one host core: react `ncells_j` j-lines of the workload with the CPU implementation."""
-    kind, mech, reactor, n, j_lo, j_hi, reps, rtol, atol, max_order, dt, states = args
+    kind, mech, reactor, n, j_lo, j_hi, reps, rtol, atol, max_order, dt, states = args[:12]
+    want_state = len(args) > 12 and args[12]
     devnull = os.open(os.devnull, os.O_WRONLY)
     os.dup2(devnull, 1)  # the reference prints banners on stdout
     from oracle.pyoracle import Oracle, Reference, reacteval_states
@@ -86,6 +96,7 @@ def _cpu_worker(args):
     idx = np.arange(j_lo, j_hi)
     t0 = time.perf_counter()
     cells = 0
+    keep = None
     for _ in range(reps):
         s = full.take(idx)
         if reactor == "ReactorCvode":
@@ -93,6 +104,10 @@ def _cpu_worker(args):
         else:
             lib.react_rk64(s, dt, atol=atol)
         cells += len(idx)
+        if want_state and keep is None:
+            keep = (s.rY.copy(), s.T.copy())
+    if want_state:
+        return cells, time.perf_counter() - t0, keep
     return cells, time.perf_counter() - t0
 
 
@@ -108,7 +123,7 @@ def cpu_throughput(a, seconds):
     ctx = mp.get_context("spawn")
     with ctx.Pool(1) as p:
         ns = n if a.states == "reacteval" else 2048
-        c0, t0 = p.map(_cpu_worker, [(kind, a.mech, a.reactor, n, 0, ns, 1, a.rtol, a.atol, a.max_order, a.dt, a.states)])[0]
+        c0, t0, ref_state = p.map(_cpu_worker, [(kind, a.mech, a.reactor, n, 0, ns, 1, a.rtol, a.atol, a.max_order, a.dt, a.states, True)])[0]
     per_sweep = max(t0, 1e-6)
     reps = max(1, int(seconds / per_sweep))
     jobs = [(kind, a.mech, a.reactor, n, 0, ns, reps, a.rtol, a.atol, a.max_order, a.dt, a.states) for _ in range(cores)]
@@ -123,6 +138,7 @@ def cpu_throughput(a, seconds):
         "sample": "%d processes x %d sweeps of the %d distinct cell states of the workload "
                   "= %d cell integrations in %.1f s" % (cores, reps, ns, cells, wall),
         "per_core": cells / tmax / cores,
+        "ref_state": ref_state,  # (rY [N, ns], T [ns]) after one call on the ns distinct states: the checker of the GPU result
     }
 
 
@@ -135,7 +151,7 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": None, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a)},
+        "config": config_of(a),
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -331,10 +347,7 @@ def run_b200(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "mechanism": a.mech, "reactor": a.reactor,
-                       "cells_per_gpu_per_step": ncell, "sharding": "one %d^3 box per GPU, no data-path collective" % n,
-                       "l2": "each step reads/writes a fresh %.0f MB copy of the state (> 126 MB L2)"
-                             % ((2 * N + 6) * 8 * ncell / 1e6)},
+            "config": config_of(a),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "prx_react_box_host (C ABI, pinned host buffers)",
                     "ms_per_step": t_e2e / e2e_steps * 1e3,
@@ -363,6 +376,22 @@ def run_b200(a):
         if not a.no_cpu_baseline:
             cb = cpu_throughput(a, a.cpu_seconds)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            if a.states == "reacteval" and cb.get("ref_state") is not None:
+                # result check of the TIMED data: the j-line (i = 0, k = 0) of the last timed step against the CPU leg's result
+                # for the same 128 states (checker only; the parity tests proper are tests/ -m gpu)
+                ref_rY, ref_T = cb["ref_state"]
+                last = bufs[a.warmup + a.steps - 1]
+                got_rY = last["rY"][:, 0, :, 0].cpu().numpy()
+                got_T = last["T"][0, 0, :, 0].cpu().numpy()
+                if a.reactor == "ReactorCvode":
+                    lim = 10.0 * (a.atol + a.rtol * np.abs(ref_rY))
+                    worst = float((np.abs(got_rY - ref_rY) / lim).max())
+                else:
+                    rho = ref_rY.sum(axis=0, keepdims=True)
+                    worst = float((np.abs(got_rY - ref_rY) / np.maximum(np.abs(ref_rY), 1e-2 * rho)).max() / 1e-10)
+                line["result_check"] = {"cells": int(ref_T.size), "against": "cpu_baseline (" + cb["kind"] + ")",
+                                        "max_dY_over_bar": worst, "max_rel_dT": float((np.abs(got_T - ref_T) / ref_T).max()),
+                                        "ok": bool(worst <= 1.0)}
         print(json.dumps(line))
     r.close()
     if world > 1:

@@ -61,7 +61,7 @@ struct Grp
 
 // ---- storage policy of the integrator state machine (prx_integrators.cuh) -------------------------
 // One contiguous block of shared memory per cell:
-//   [ (nz + 6) vectors of NEQ | sc N | gs N | dq N | qv NR | A NEQ*NEQ | piv NEQ ints ]
+//   [ (nz + 6) vectors of NEQ | sc N | gs N | dq N | qv NR | piv NEQ ints | perm NEQ ints | A NEQ*NEQ ]
 // savedJ (read once per linear setup) lives in a global scratch slot of the group (L2 resident).
 template <int G>
 struct BdfStoreCoop
@@ -77,7 +77,7 @@ struct BdfStoreCoop
   // slot instead, which quadruples the number of resident warps; its accesses are coalesced column segments
   __host__ __device__ static int doubles_per_cell(const int qmax, const bool a_global)
   {
-    int d = (qmax + 1 + 6) * NEQ + 3 * N + PRX_NUM_REACTIONS + (NEQ + 1) / 2 + (a_global ? 0 : NEQ * NEQ);
+    int d = (qmax + 1 + 6) * NEQ + 3 * N + PRX_NUM_REACTIONS + 2 * ((NEQ + 1) / 2) + (a_global ? 0 : NEQ * NEQ);
     if (G < 32) { // cells of one warp start 8 doubles apart modulo 16: their G-wide rows use distinct banks
       while ((d & 15) != 8) {
         d++;
@@ -98,7 +98,8 @@ struct BdfStoreCoop
   PRX_MEM double* dq() const { return gs() + N; }
   PRX_MEM double* qv() const { return dq() + N; }
   PRX_MEM int* piv() const { return reinterpret_cast<int*>(qv() + PRX_NUM_REACTIONS); }
-  PRX_MEM Mat A() const { return gA != nullptr ? gA : (qv() + PRX_NUM_REACTIONS + (NEQ + 1) / 2); }
+  PRX_MEM int* perm() const { return piv() + 2 * ((NEQ + 1) / 2); } // composed row permutation (one-warp-per-matrix solve)
+  PRX_MEM Mat A() const { return gA != nullptr ? gA : (qv() + PRX_NUM_REACTIONS + 2 * ((NEQ + 1) / 2)); }
   PRX_MEM double* savedJ() const { return gJ; }
   // cooperative hooks
   PRX_MEM int vbegin() const { return g.gl; }
@@ -301,9 +302,219 @@ __device__ __forceinline__ void getrs_coop(
   g.sync();
 }
 
+// ---- one WARP per matrix (G = 32): lean forms ------------------------------------------------------------------
+// ncu r02h on dodecane_lu (54 x 54): getrf_coop + getrs_coop were 66 % of the executed instructions - 75 k warp instructions
+// per factorisation for 3.3 k useful FMAs per lane, 6.7 k per solve for 180 - most of it predicates, clamps and 64-bit index
+// arithmetic of the generic batched loops, plus a shared-memory round trip and a group barrier per elimination step.  Here
+// lane l owns rows l and l + 32 in REGISTERS for the duration of a column / a solve; the pivot row and the solution entries
+// travel by shuffle; columns are walked with running pointers; the row interchanges of a solve are one gather through the
+// composed permutation the factorisation leaves behind.  Same pivot choice (first row of maximal magnitude), same per-entry
+// operations in the same order as getrf_coop / getrs_coop (= SUNDlsMat_denseGETRF / denseGETRS, sundials_dense.c:82-190).
+__device__ __forceinline__ int getrf_warp(double* __restrict__ a, int* __restrict__ piv, int* __restrict__ perm)
+{
+  static_assert(NEQ <= 64, "two rows per lane");
+  constexpr unsigned FULLW = 0xffffffffu;
+  const int l = (int)(threadIdx.x & 31u);
+  const int r1 = l + 32;
+  const bool has1 = r1 < NEQ;
+  __syncwarp();
+  for (int i = l; i < NEQ; i += 32) {
+    perm[i] = i;
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int k = 0; k < NEQ; k++) {
+    double* ck = a + k * NEQ;
+    const double c0 = (l >= k && l < NEQ) ? ck[l] : 0.0;
+    const double c1 = (has1 && r1 >= k) ? ck[r1] : 0.0;
+    // arg-max of |column k| over rows >= k, ties to the lowest row
+    double best = -1.0;
+    int bi = k;
+    if (l >= k && l < NEQ) {
+      best = fabs(c0);
+      bi = l;
+    }
+    if (has1 && r1 >= k && fabs(c1) > best) {
+      best = fabs(c1);
+      bi = r1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(FULLW, best, o);
+      const int oi = __shfl_xor_sync(FULLW, bi, o);
+      if (ob > best || (ob == best && oi < bi)) {
+        best = ob;
+        bi = oi;
+      }
+    }
+    const int p = (best < 0.0) ? k : bi; // all-NaN column: the reference keeps l = k
+    if (l == 0) {
+      piv[k] = p;
+    }
+    if (best == 0.0) {
+      __syncwarp();
+      return k + 1;
+    }
+    if (p != k) { // interchange rows k and p in every column (lane j: columns j, j + 32) and in the composed permutation
+      for (int j = l; j < NEQ; j += 32) {
+        const double t = a[j * NEQ + p];
+        a[j * NEQ + p] = a[j * NEQ + k];
+        a[j * NEQ + k] = t;
+      }
+      if (l == 0) {
+        const int t = perm[k];
+        perm[k] = perm[p];
+        perm[p] = t;
+      }
+      __syncwarp();
+    }
+    // multipliers of this lane's rows (column k below the diagonal, after the interchange)
+    const double akk = ck[k];
+    const double mult = 1.0 / akk;
+    double v0 = c0, v1 = c1; // this lane's entries of column k after the interchange
+    if (p != k) {
+      v0 = (l >= k && l < NEQ) ? ck[l] : 0.0;
+      v1 = (has1 && r1 >= k) ? ck[r1] : 0.0;
+    }
+    const bool u0 = (l > k) && (l < NEQ), u1 = has1 && (r1 > k);
+    const double m0 = u0 ? v0 * mult : 0.0, m1 = u1 ? v1 * mult : 0.0;
+    if (u0) {
+      ck[l] = m0;
+    }
+    if (u1) {
+      ck[r1] = m1;
+    }
+    // rank-1 update of the trailing columns, PRX_LU_CB at a time (loads of a batch before its stores)
+#ifndef PRX_LU_CB
+#define PRX_LU_CB 4
+#endif
+    double* cj = ck + NEQ;
+    int j = k + 1;
+#pragma unroll 1
+    for (; j + PRX_LU_CB <= NEQ; j += PRX_LU_CB, cj += PRX_LU_CB * NEQ) {
+      double akj[PRX_LU_CB], x0[PRX_LU_CB], x1[PRX_LU_CB];
+#pragma unroll
+      for (int c = 0; c < PRX_LU_CB; c++) {
+        akj[c] = cj[c * NEQ + k];
+        x0[c] = u0 ? cj[c * NEQ + l] : 0.0;
+        x1[c] = u1 ? cj[c * NEQ + r1] : 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < PRX_LU_CB; c++) {
+        if (akj[c] != 0.0) {
+          if (u0) {
+            cj[c * NEQ + l] = x0[c] - akj[c] * m0;
+          }
+          if (u1) {
+            cj[c * NEQ + r1] = x1[c] - akj[c] * m1;
+          }
+        }
+      }
+    }
+#pragma unroll 1
+    for (; j < NEQ; j++, cj += NEQ) {
+      const double akj = cj[k];
+      if (akj != 0.0) {
+        if (u0) {
+          cj[l] = cj[l] - akj * m0;
+        }
+        if (u1) {
+          cj[r1] = cj[r1] - akj * m1;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  return 0;
+}
+
+__device__ __forceinline__ void getrs_warp(const double* __restrict__ a, const int* __restrict__ perm, double* __restrict__ b)
+{
+  constexpr unsigned FULLW = 0xffffffffu;
+  constexpr int CB = 6;
+  const int l = (int)(threadIdx.x & 31u);
+  const int r1 = l + 32;
+  const bool has0 = l < NEQ, has1 = r1 < NEQ;
+  __syncwarp();
+  // all row interchanges at once: b <- P b through the composed permutation
+  double b0 = has0 ? b[perm[l]] : 0.0;
+  double b1 = has1 ? b[perm[r1]] : 0.0;
+  // L y = b
+#pragma unroll 1
+  for (int k0 = 0; k0 < NEQ - 1; k0 += CB) {
+    double l0[CB], l1[CB];
+#pragma unroll
+    for (int c = 0; c < CB; c++) {
+      const int k = k0 + c;
+      const bool in = k < NEQ - 1;
+      l0[c] = (in && has0 && l > k) ? a[k * NEQ + l] : 0.0;
+      l1[c] = (in && has1 && r1 > k) ? a[k * NEQ + r1] : 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < CB; c++) {
+      const int k = k0 + c;
+      if (k < NEQ - 1) {
+        const double bk = __shfl_sync(FULLW, (k < 32) ? b0 : b1, k & 31);
+        if (has0 && l > k) {
+          b0 -= l0[c] * bk;
+        }
+        if (has1 && r1 > k) {
+          b1 -= l1[c] * bk;
+        }
+      }
+    }
+  }
+  // U x = y, from the last column
+#pragma unroll 1
+  for (int k0 = NEQ - 1; k0 >= 0; k0 -= CB) {
+    double u0[CB], u1[CB], dv[CB];
+#pragma unroll
+    for (int c = 0; c < CB; c++) {
+      const int k = k0 - c;
+      const bool in = k >= 0;
+      dv[c] = in ? a[k * NEQ + k] : 1.0;
+      u0[c] = (in && has0 && l < k) ? a[k * NEQ + l] : 0.0;
+      u1[c] = (in && has1 && r1 < k) ? a[k * NEQ + r1] : 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < CB; c++) {
+      const int k = k0 - c;
+      if (k >= 0) {
+        const double bk = __shfl_sync(FULLW, (k < 32) ? b0 : b1, k & 31) / dv[c];
+        if (has0 && l < k) {
+          b0 -= u0[c] * bk;
+        }
+        if (has1 && r1 < k) {
+          b1 -= u1[c] * bk;
+        }
+        if (l == k) {
+          b0 = bk;
+        }
+        if (r1 == k) {
+          b1 = bk;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  if (has0) {
+    b[l] = b0;
+  }
+  if (has1) {
+    b[r1] = b1;
+  }
+  __syncwarp();
+}
+
 template <int G>
 PRX_MEM void BdfStoreCoop<G>::getrs(const double* a, const int* p, double* b) const
 {
+#ifndef PRX_COOP_GENERIC_LA
+  if (G == 32 && NEQ > 32 && NEQ <= 64) {
+    getrs_warp(a, perm(), b);
+    return;
+  }
+#endif
   getrs_coop<G>(g, a, p, b);
 }
 
@@ -426,8 +637,29 @@ __device__ __forceinline__ void rhs_coop(
   for (int n = g.gl; n < N; n += G) {
     double w = 0.0;
     const int j1 = TB::sp_ptr(n + 1);
+    int j = TB::sp_ptr(n);
+    // the gather list (reaction index, coefficient) and the rates are fetched four terms ahead of the sequential sum
+    // (ncu r02h: the one-term-at-a-time chain table load -> shared-memory load -> FMA was 9 % of dodecane_lu's stall samples)
 #pragma unroll 1
-    for (int j = TB::sp_ptr(n); j < j1; j++) {
+    for (; j + 4 <= j1; j += 4) {
+      int rr[4];
+      double cc[4], qq[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        rr[u] = TB::sp_r(j + u);
+        cc[u] = (double)TB::sp_c(j + u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        qq[u] = qv[rr[u]];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        w = w + cc[u] * qq[u];
+      }
+    }
+#pragma unroll 1
+    for (; j < j1; j++) {
       w = w + (double)TB::sp_c(j) * qv[TB::sp_r(j)];
     }
     w *= 1.0e-6;

@@ -17,6 +17,7 @@
 //                arithmetic, only when it happens.
 // HBM traffic is only the boundary arrays: (2N+3) doubles in, (N+3) out per cell.
 #include <cstdio>
+#include <cstdlib>
 
 #include "prx_integrators.cuh"
 #include "prx_tchem.cuh"
@@ -1495,7 +1496,8 @@ __global__ void __launch_bounds__(32 * W, (PRX_COOP_MINBLOCKS / W) > 0 ? (PRX_CO
     if (cell >= 0 && req == REQ_NONE) {
       req = bdf_resume(s, pc);
     }
-    if (W > 1) {
+    if (W > 1) { // (making this barrier optional at run time - PRX_COOP_BARRIERS, session r02n - cost 23 % by itself and the
+                 // one-barrier mode was no faster: unconditional)
       __syncthreads(); // phase barrier: the block's warps enter the RHS / Jacobian / LU service together
     } else {
       __syncwarp();
@@ -1531,7 +1533,14 @@ __global__ void __launch_bounds__(32 * W, (PRX_COOP_MINBLOCKS / W) > 0 ? (PRX_CO
     }
     if (m_lu && ((__popc(m_lu) >= sp.lu_defer_min_lanes * G) || (m_rhs == 0))) {
       if (req == REQ_LU) {
-        s.lu_info = getrf_coop<G>(g, s.A(), s.piv());
+#ifndef PRX_COOP_GENERIC_LA
+        if (G == 32 && NEQ > 32 && NEQ <= 64) {
+          s.lu_info = getrf_warp(s.A(), s.piv(), s.perm()); // one warp per matrix, rows in registers (prx_coop.cuh)
+        } else
+#endif
+        {
+          s.lu_info = getrf_coop<G>(g, s.A(), s.piv());
+        }
         req = REQ_NONE;
       }
       __syncwarp();
@@ -1841,6 +1850,35 @@ __global__ void PRX_CAT(compute_temp_kernel_, PRX_MECH_SUFFIX)(const BoxArgs a)
   }
 }
 
+// Same, two cells (consecutive in i) per thread with 128-bit loads / stores: every component row is read as double2
+// (north_star: "SoA state is read with coalesced, vectorised HBM loads").  Used when the rows are 16-byte aligned and of even
+// length (launch_compute_temp checks); small mechanisms only (two cells of mass fractions in registers).
+#define PRX_HAVE_CT2 (PRX_NUM_SPECIES <= 24)
+#if PRX_HAVE_CT2
+__global__ void PRX_CAT(compute_temp2_kernel_, PRX_MECH_SUFFIX)(const BoxArgs a)
+{
+  const int npair = a.ncells >> 1;
+  for (int pr = blockIdx.x * blockDim.x + threadIdx.x; pr < npair; pr += gridDim.x * blockDim.x) {
+    double* S = a.snew.p + cell_offset(pr << 1, a.len, a.snew.js, a.snew.ks); // len[0] even: both cells on one row
+    const long long ns = a.snew.ns;
+    const double2 rho = *reinterpret_cast<const double2*>(S + a.ix.urho * ns);
+    const double2 re = *reinterpret_cast<const double2*>(S + a.ix.ueint * ns);
+    double2 T = *reinterpret_cast<const double2*>(S + a.ix.utemp * ns);
+    const double ia = 1.0 / rho.x, ib = 1.0 / rho.y;
+    double Ya[N], Yb[N];
+#pragma unroll
+    for (int n = 0; n < N; n++) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(S + (a.ix.ufs + n) * ns));
+      Ya[n] = v.x * ia;
+      Yb[n] = v.y * ib;
+    }
+    t_from_energy<1>(re.x * ia, Ya, T.x);
+    t_from_energy<1>(re.y * ib, Yb, T.y);
+    *reinterpret_cast<double2*>(S + a.ix.utemp * ns) = T;
+  }
+}
+#endif
+
 cudaError_t launch_compute_temp(const BoxArgs& a, cudaStream_t stream)
 {
   if (a.ncells <= 0) {
@@ -1849,8 +1887,24 @@ cudaError_t launch_compute_temp(const BoxArgs& a, cudaStream_t stream)
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long want = ((long long)a.ncells + 255) / 256;
   const long long cap = (long long)sms * 8; // a multiple of the SM count; grid-stride beyond it
+#if PRX_HAVE_CT2
+  // Measured (session r02o, 256^3 FAB): 0.843 vs 0.823 ms (LiDryer), 2.09 vs 1.73 ms (drm19) - the kernel is bound by issue
+  // slots / the FP64 pipe (T-Newton), not by its loads, and two cells per thread cost registers: the 128-bit form is OFF
+  // unless PRX_CT_VEC2=1 (tests/test_gpu_state.py exercises both).
+  static const bool want_vec2 = [] {
+    const char* e = std::getenv("PRX_CT_VEC2");
+    return e != nullptr && e[0] == '1';
+  }();
+  const bool vec2 = want_vec2 && (a.len[0] % 2 == 0) && (reinterpret_cast<unsigned long long>(a.snew.p) % 16 == 0) && (a.snew.js % 2 == 0) &&
+                    (a.snew.ks % 2 == 0) && (a.snew.ns % 2 == 0);
+  if (vec2) {
+    const long long want = ((long long)(a.ncells >> 1) + 255) / 256;
+    PRX_CAT(compute_temp2_kernel_, PRX_MECH_SUFFIX)<<<(int)(want < cap ? want : cap), 256, 0, stream>>>(a);
+    return cudaGetLastError();
+  }
+#endif
+  const long long want = ((long long)a.ncells + 255) / 256;
   PRX_CAT(compute_temp_kernel_, PRX_MECH_SUFFIX)<<<(int)(want < cap ? want : cap), 256, 0, stream>>>(a);
   return cudaGetLastError();
 }

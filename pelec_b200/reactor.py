@@ -366,11 +366,17 @@ class ReactorB200:
 
     def probe_rhs(self, t, y, rhoe, rhoesrc, rYsrc):
         import numpy as np
+        # contiguous float64 copies held in locals until the call returns (a temporary's .ctypes.data would dangle)
         y = np.ascontiguousarray(y, dtype=np.float64)
+        rhoe = np.ascontiguousarray(rhoe, dtype=np.float64)
+        rhoesrc = np.ascontiguousarray(rhoesrc, dtype=np.float64)
+        rYsrc = np.ascontiguousarray(rYsrc, dtype=np.float64)
+        n = y.shape[0]
+        if rhoe.size != n or rhoesrc.size != n or rYsrc.size != n * self.N or y.shape[1] != self.N + 1:
+            raise PrxError(-1, "probe_rhs: array shapes do not match (n, NUM_SPECIES+1)")
         out = np.zeros_like(y)
         self._check(self.lib.prx_probe_rhs_host(
-            self.h, y.shape[0], float(t), y.ctypes.data, np.ascontiguousarray(rhoe).ctypes.data,
-            np.ascontiguousarray(rhoesrc).ctypes.data, np.ascontiguousarray(rYsrc).ctypes.data, out.ctypes.data))
+            self.h, n, float(t), y.ctypes.data, rhoe.ctypes.data, rhoesrc.ctypes.data, rYsrc.ctypes.data, out.ctypes.data))
         return out
 
     def probe_jac(self, y):

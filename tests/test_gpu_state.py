@@ -232,11 +232,15 @@ def test_react_state_boxes_equals_box_by_box():
 
 
 @pytest.mark.parametrize("mech", ["LiDryer", "drm19", "dodecane_lu"])
-def test_compute_temp_matches_oracle_rey2t(mech):
-    """pc_cmpTemp (PC/Source/Utilities.H:70-84): T <- REY2T(rho, e, Y) in place, on a ragged box inside a padded, offset FAB."""
+@pytest.mark.parametrize("layout", ["ragged", "aligned"])
+def test_compute_temp_matches_oracle_rey2t(mech, layout):
+    """pc_cmpTemp (PC/Source/Utilities.H:70-84): T <- REY2T(rho, e, Y) in place, on a box inside a padded, offset FAB: a ragged
+    one (odd row length, misaligned rows: scalar loads) and an even, 16-byte aligned one (the 128-bit load path)."""
     orc = Oracle(mech)
     dev = torch.device("cuda:0")
-    shape, pad, begin = (37, 5, 3), (1, 2, 0), (4, -3, 0)
+    shape, pad, begin = ((37, 5, 3), (1, 2, 0), (4, -3, 0)) if layout == "ragged" else ((64, 4, 2), (2, 1, 1), (-6, 0, 3))
+    # (the 128-bit form is selected by PRX_CT_VEC2=1, read once per process: covered when the suite runs with it set,
+    #  tools/gpu_r02p.sh; results are identical either way)
     sold, _, _ = make_state(orc, shape, 3)
     rng = np.random.default_rng(5)
     sold[6] += rng.uniform(-150, 150, sold.shape[1])  # a poor guess
