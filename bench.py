@@ -49,6 +49,7 @@ def parse():
                          "(tests/golden/pmf_states_<mech>.npz, SURVEY 8(d) set B: the divergent workload)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference's own GPU path (second stated baseline)")
     ap.add_argument("--strong", default="auto",
                     help="sharded-domain (strong scaling) blocks added to the JSON line: 'auto' = BASELINE configs[2] "
                          "(256^3 drm19, max_grid_size 64) at every N and configs[3] (128^3 dodecane_lu, max_grid_size 32) at "
@@ -392,10 +393,33 @@ def run_b200(a):
                 line["result_check"] = {"cells": int(ref_T.size), "against": "cpu_baseline (" + cb["kind"] + ")",
                                         "max_dY_over_bar": worst, "max_rel_dT": float((np.abs(got_T - ref_T) / ref_T).max()),
                                         "ok": bool(worst <= 1.0)}
+        if world == 1 and not a.no_ref_gpu:
+            line["ref_gpu_baseline"] = ref_gpu_baseline(a)
         print(json.dumps(line))
     r.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def ref_gpu_baseline(a):
+    """Second stated baseline (measurement infrastructure, like cpu_baseline): the UNMODIFIED reference's own GPU reactor
+    (oracle/_ref/libpeleref_gpu_<mech>.so, built for sm_100a by oracle/ref_gpu/Makefile) on the same workload and the same GPU,
+    in its own process (tools/ref_gpu_bench.py), CUDA-event timed around ReactorBase::react with device-resident FABs.
+    ReactorCvode on a GPU integrates the whole box as ONE coupled CVODE system with matrix-free GMRES (the reference's
+    GPU default, ReactEval inputs.3d_Array4) - not the per-cell dense-direct semantics of its CPU path that this repo reproduces."""
+    script = os.path.join(ROOT, "tools", "ref_gpu_bench.py")
+    cmd = [sys.executable, script, "--mech", a.mech, "--n", str(a.n), "--reactor", a.reactor, "--rtol", repr(a.rtol),
+           "--atol", repr(a.atol), "--max-order", str(a.max_order), "--dt", repr(a.dt), "--reps", "3", "--check"]
+    try:
+        out = subprocess.run(cmd, capture_output=True, timeout=300, text=True)
+        d = json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:  # the baseline is optional; the product line must not depend on it
+        return {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+    if "unavailable" in d:
+        return {"unavailable": d["unavailable"]}
+    return {"value": d["value"], "unit": d["unit"], "kind": "reference-gpu", "ms_per_step": d["ms_best"],
+            "solve_type": d["solve_type"], "react_return": d["react_return"], "check_vs_cpu_semantics": d["check"],
+            "sample": "%s box, best of %d ReactorBase::react calls, device-resident" % (d["box"], len(d["ms_per_call"]))}
 
 
 def profile_states(mech, n):

@@ -1,0 +1,54 @@
+"""The drop-in IN THE APPLICATION: the unmodified PeleC (PMF regression case, two AMR levels, hydro +
+diffusion + reactions, SDC) is advanced with the reference's ReactorCvode / ReactorRK64 and, in a second process, with
+pelec.chem_integrator = ReactorCvodeB200 / ReactorRK64B200 - the reference's own factory creating this repo's reactor, and
+PeleC::react_state (PC/Source/React.cpp:222-230) driving the CUDA kernels through the reference's virtual react().
+The two runs must produce the same hierarchy and the same state.
+
+Needs oracle/_ref/libpelec_pmf_LiDryer.so (built in the build container by oracle/ref_pelec/Makefile; travels to the GPU box)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "oracle", "_ref", "libpelec_pmf_LiDryer.so")
+NSTEPS = 4
+
+
+def run(integ, tmp_path, extra=()):
+    out = str(tmp_path / (integ + ".npz"))
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "pelec_pmf_run.py"), integ, str(NSTEPS), out] + list(extra),
+                       capture_output=True, text=True, timeout=900)
+    assert "PELEC_PMF_DONE" in p.stdout, (p.stdout[-2000:], p.stderr[-2000:])
+    assert "Creating ReactorBase instance: " + integ in p.stdout  # the reference's factory (Factory.H) announces what it creates
+    z = np.load(out)
+    return {k: z[k] for k in z.files}
+
+
+@pytest.mark.skipif(not os.path.exists(LIB), reason="oracle/_ref/libpelec_pmf_LiDryer.so not built")
+@pytest.mark.parametrize("stock,ours,tol", [("ReactorCvode", "ReactorCvodeB200", 1e-8), ("ReactorRK64", "ReactorRK64B200", 1e-9)])
+def test_pmf_with_b200_reactor_matches_stock_pelec(stock, ours, tol, tmp_path):
+    ode = ["ode.rtol=1e-8", "ode.atol=1e-10", "cvode.max_order=3"]
+    a = run(stock, tmp_path, ode)
+    b = run(ours, tmp_path, ode)
+    assert a["finest"] == b["finest"] >= 1 and a["time"] == b["time"]  # same dt sequence (CFL + reactions)
+    worst = {}
+    for lev in range(int(a["finest"]) + 1):
+        assert np.array_equal(a["boxes%d" % lev], b["boxes%d" % lev])  # same regridding
+        sa, sb = a["S%d" % lev], b["S%d" % lev]
+        for c in range(sa.shape[0]):
+            scale = np.abs(sa[c]).max()
+            if c >= 7:
+                scale = max(scale, 1e-6 * np.abs(sa[0]).max())  # species: against max(rhoY_k, 1e-6 rho)
+            if c in (1, 2):
+                scale = max(scale, np.abs(sa[3]).max())  # transverse momenta: against the axial one
+            worst[(lev, c)] = float(np.abs(sa[c] - sb[c]).max() / scale)
+        # heat release (I_R's last component): the quantity PeleC plots as the flame marker
+        hr = np.abs(a["IR%d" % lev][-1]).max()
+        worst[(lev, "heatRelease")] = float(np.abs(a["IR%d" % lev][-1] - b["IR%d" % lev][-1]).max() / hr)
+    print("PMF %s vs %s after %d coarse steps: worst relative difference %.2e (%s); wall %.1f s vs %.1f s" % (
+        stock, ours, NSTEPS, max(worst.values()), max(worst, key=worst.get), float(a["wall_s"]), float(b["wall_s"])))
+    assert max(worst.values()) <= tol, worst
