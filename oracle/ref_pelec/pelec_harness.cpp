@@ -16,6 +16,7 @@
 #include <AMReX_Amr.H>
 #include <AMReX_AmrLevel.H>
 #include <AMReX_EB2.H>
+#include <AMReX_Gpu.H>
 #include <AMReX_MultiFab.H>
 #include <AMReX_ParmParse.H>
 
@@ -66,6 +67,34 @@ which_mf(int lev, int which)
   default:
     return l.get_new_data(Reactions_Type);
   }
+}
+
+// CUDA build (Makefile.cuda): the level's data is device memory; the host loops below then run on a pinned-memory copy
+// (host_copy / push_back), never on the level's own FABs
+amrex::MultiFab
+host_copy(const amrex::MultiFab& mf, bool with_data)
+{
+#ifdef AMREX_USE_GPU
+  amrex::MultiFab h(mf.boxArray(), mf.DistributionMap(), mf.nComp(), 0, amrex::MFInfo().SetArena(amrex::The_Pinned_Arena()));
+#else
+  amrex::MultiFab h(mf.boxArray(), mf.DistributionMap(), mf.nComp(), 0);
+#endif
+  if (with_data) {
+    amrex::MultiFab::Copy(h, mf, 0, 0, mf.nComp(), 0);
+  }
+#ifdef AMREX_USE_GPU
+  amrex::Gpu::Device::synchronize();
+#endif
+  return h;
+}
+
+void
+push_back(amrex::MultiFab& mf, const amrex::MultiFab& h)
+{
+  amrex::MultiFab::Copy(mf, h, 0, 0, mf.nComp(), 0);
+#ifdef AMREX_USE_GPU
+  amrex::Gpu::Device::synchronize();
+#endif
 }
 
 template <class F>
@@ -206,7 +235,7 @@ pelecref_get(int lev, int which, double* out)
   if (which == 0 && !level(lev).get_state_data(State_Type).hasOldData()) {
     level(lev).get_state_data(State_Type).allocOldData();
   }
-  const amrex::MultiFab& mf = which_mf(lev, which);
+  const amrex::MultiFab mf = host_copy(which_mf(lev, which), true);
   const long nc = pelecref_ncells(lev);
   const int ncomp = mf.nComp();
   for_cells(mf, [&](const amrex::MFIter& mfi, int i, int j, int k, long c) {
@@ -223,7 +252,8 @@ pelecref_set(int lev, int which, const double* in)
   if (which == 0 && !level(lev).get_state_data(State_Type).hasOldData()) {
     level(lev).get_state_data(State_Type).allocOldData();
   }
-  amrex::MultiFab& mf = which_mf(lev, which);
+  amrex::MultiFab& dst = which_mf(lev, which);
+  amrex::MultiFab mf = host_copy(dst, false);
   const long nc = pelecref_ncells(lev);
   const int ncomp = mf.nComp();
   for_cells(mf, [&](const amrex::MFIter& mfi, int i, int j, int k, long c) {
@@ -232,6 +262,7 @@ pelecref_set(int lev, int which, const double* in)
       a(i, j, k, n) = in[n * nc + c];
     }
   });
+  push_back(dst, mf);
 }
 
 // PeleC::react_state(time, dt, react_init, &aux_src) on level lev; aux_src [NVAR][ncells] = the non-reacting source the MOL /
@@ -245,12 +276,14 @@ pelecref_react_state(int lev, double dt, int react_init, const double* aux)
   src.setVal(0.0);
   if (aux != nullptr) {
     const long nc = pelecref_ncells(lev);
-    for_cells(src, [&](const amrex::MFIter& mfi, int i, int j, int k, long c) {
-      auto const& a = src.array(mfi);
+    amrex::MultiFab hsrc = host_copy(src, false);
+    for_cells(hsrc, [&](const amrex::MFIter& mfi, int i, int j, int k, long c) {
+      auto const& a = hsrc.array(mfi);
       for (int n = 0; n < NVAR; ++n) {
         a(i, j, k, n) = aux[n * nc + c];
       }
     });
+    push_back(src, hsrc);
   }
   l.react_state(pelecref_time(lev), dt, react_init != 0, react_init != 0 ? nullptr : &src);
 }

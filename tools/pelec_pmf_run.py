@@ -2,7 +2,7 @@
 """TEST INFRASTRUCTURE: run the UNMODIFIED PeleC application (PMF regression case, oracle/_ref/libpelec_pmf_<mech>.so built by
 oracle/ref_pelec/Makefile) for n coarse time steps with a given pelec.chem_integrator and dump every level's state.
 
-  python tools/pelec_pmf_run.py <integrator> <nsteps> <out.npz> [name=value ...]
+  python tools/pelec_pmf_run.py <integrator> <nsteps> <out.npz> [--cuda] [name=value ...]
 
 The library also holds integration/ReactorB200.cpp, so <integrator> may be ReactorCvodeB200 / ReactorRK64B200: the reference's
 own factory then creates this repo's reactor and PeleC::react_state (PC/Source/React.cpp:222-230) drives the CUDA kernels
@@ -25,7 +25,12 @@ def main():
     extra = sys.argv[4:]
     mech = "LiDryer"
     case = os.path.join(ROOT, "oracle", "_ref", "pmf_case")
-    lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libpelec_pmf_%s.so" % mech))
+    # --cuda: the CUDA build of the application (oracle/ref_pelec/Makefile.cuda; AMReX, PeleC, PelePhysics compiled with nvcc
+    # for sm_100a): state in device memory, the shim's AMREX_USE_GPU branch hands device pointers to prx_react_box
+    cuda = "--cuda" in extra
+    if cuda:
+        extra = [e for e in extra if e != "--cuda"] + ["amrex.the_arena_init_size=0", "amrex.abort_on_out_of_gpu_memory=1"]
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libpelec_pmf_%s%s.so" % ("cuda_" if cuda else "", mech)))
     os.chdir(tempfile.mkdtemp(prefix="pelec_pmf_"))
     args = ["pelec", os.path.join(case, "pmf-lidryer-cvode.inp"), "amr.plot_files_output=0", "amr.checkpoint_files_output=0",
             "pelec.xNormPlane.int=100000", "prob.pmf_datafile=" + os.path.join(case, "LiDryer_H2_p1_phi0_4000tu0300.dat"),
