@@ -182,6 +182,30 @@ PRX_API int prx_compute_temp_boxes(
   void* cuda_stream);
 
 
+/* ---- PeleC's conserved -> primitive conversion (PC/Source/Utilities.H:242-321 pc_ctoprim; called per box by
+ * PeleC::getMOLSrcTerm / the Godunov driver, PC/Source/Hydro.cpp, PC/Source/MOL.cpp) ----
+ * For every cell of every box: q = (rho, u, v, w, gamma_e, p, rho*e, T, Y_k), qaux = (gamma_c, c, c_small, dp/drho|e, dp/de|rho,
+ * R_specific) from the conserved state u, with the Fuego EOS (T from (e, Y) by GET_T_GIVEN_EY with u(UTEMP) as the guess;
+ * |Y_k| < 1e-4 eps flushed to zero as the reference does).  No rotating frame (omega = 0), NUM_ADV = NUM_AUX = NUM_LIN = 0.
+ * DEVICE pointers, asynchronous on cuda_stream.  SURVEY.md 8f-3. */
+typedef struct prx_prim_index {
+  int qrho, qu, qv, qw, qgame, qpres, qreint, qtemp, qfs, qvar;   /* PC/Source/IndexDefines.H: QRHO ... QFS, QVAR */
+  int qgamc, qc, qcsml, qdpdr, qdpde, qrspec, nqaux;              /* QGAMC ... QRSPEC, NQAUX */
+} prx_prim_index;
+
+PRX_API int prx_ctoprim_boxes(
+  prx_handle* h, int nboxes, const int* lo, const int* hi, const prx_array4* u, const prx_array4* q, const prx_array4* qaux,
+  const prx_state_index* ix, const prx_prim_index* qx, double small_num, void* cuda_stream);
+
+/* ---- pele::physics::transport::SimpleTransport::get_transport_coeffs (PP/Source/Transport/Simple.H:391-447; PeleC's call
+ * site PC/Source/Diffusion.cpp:182-222 with get_xi = get_mu = get_lam = get_Ddiag = true, get_chi = false) ----
+ * Y [N], T [1], rho [1] in (component-offset views of the primitive FAB are fine); D [N] (the reference's rho*D_k, as stored
+ * in coeff_cc(dComp_rhoD)), mu, xi, lam [1] out.  Fuego EOS (no Chung high-pressure corrections), Soret off. */
+PRX_API int prx_transport_boxes(
+  prx_handle* h, int nboxes, const int* lo, const int* hi, const prx_array4* Y, const prx_array4* T, const prx_array4* rho,
+  const prx_array4* D, const prx_array4* mu, const prx_array4* xi, const prx_array4* lam, void* cuda_stream);
+
+
 /* ---- ReactorBase::react, flat version (ReactorBase.H:42-54), DEVICE pointers ----
  * y [ncells*(N+1)] YCOrder (cell-major, T last), ysrc [ncells*N], e [ncells], esrc [ncells].
  * Reference semantics of the 1-D call: T is taken from y (no initial REY2T) and the

@@ -132,6 +132,24 @@ class Oracle:
         self.lib.orc_thermo(n, _p(np.ascontiguousarray(T)), _p(np.ascontiguousarray(Y)), _p(ei), _p(cv), _p(em), _p(hi))
         return ei, cv, em, hi
 
+    def ctoprim(self, u, small_num=1.0e-8):
+        """pc_ctoprim: u [NVAR, n] -> q [QVAR, n], qa [6, n] (PeleC component layout, oracle/chem_oracle.c orc_ctoprim)"""
+        u = np.ascontiguousarray(u, dtype=float)
+        n = u.shape[1]
+        q, qa = np.zeros((8 + self.N, n)), np.zeros((6, n))
+        self.lib.orc_ctoprim.argtypes = [C.c_int, dp, dp, dp, C.c_double]
+        self.lib.orc_ctoprim(n, _p(u), _p(q), _p(qa), float(small_num))
+        return q, qa
+
+    def transport(self, T, rho, Y):
+        """SimpleTransport::transport: T [n], rho [n], Y [n, N] -> D [n, N], mu, xi, lam [n]"""
+        T, rho, Y = (np.ascontiguousarray(x, dtype=float) for x in (T, rho, Y))
+        n = len(T)
+        D, mu, xi, lam = np.zeros((n, self.N)), np.zeros(n), np.zeros(n), np.zeros(n)
+        self.lib.orc_transport.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp, dp]
+        self.lib.orc_transport(n, _p(T), _p(rho), _p(Y), _p(D), _p(mu), _p(xi), _p(lam))
+        return D, mu, xi, lam
+
     def ckwc(self, T, Cc):
         w = np.zeros_like(Cc)
         self.lib.orc_ckwc(len(T), _p(np.ascontiguousarray(T)), _p(np.ascontiguousarray(Cc)), _p(w))
@@ -232,6 +250,15 @@ class Reference:
         cv, em = np.zeros(n), np.zeros(n)
         self.lib.peleref_thermo(n, _p(np.ascontiguousarray(T)), _p(np.ascontiguousarray(Y)), _p(ei), _p(cv), _p(em), _p(hi))
         return ei, cv, em, hi
+
+    def transport(self, T, rho, Y):
+        """the reference's SimpleTransport::transport (peleref_transport)"""
+        T, rho, Y = (np.ascontiguousarray(x, dtype=float) for x in (T, rho, Y))
+        n = len(T)
+        D, mu, xi, lam = np.zeros((n, self.N)), np.zeros(n), np.zeros(n), np.zeros(n)
+        self.lib.peleref_transport.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp, dp]
+        self.lib.peleref_transport(n, _p(T), _p(rho), _p(Y), _p(D), _p(mu), _p(xi), _p(lam))
+        return D, mu, xi, lam
 
     def ckwc(self, T, Cc):
         w = np.zeros_like(Cc)

@@ -26,6 +26,7 @@
 #include "mechanism.H"
 #include <PelePhysics.H>
 #include <ReactorBase.H>
+#include <Transport.H>
 
 using amrex::Real;
 using pele::physics::reactions::ReactorBase;
@@ -334,6 +335,38 @@ peleref_fkernelspec(
       pele::physics::reactions::utils::YCOrder>(
       0, 1, t, reactor_type, y + s * neq, ydot + s * neq, rhoe_init + s,
       rhoesrc_ext + s, rYsrc + s * NUM_SPECIES);
+  }
+}
+
+// SimpleTransport::transport as PeleC's diffusion driver calls it (PC/Source/Diffusion.cpp:195-222 through
+// PC/Source/TransCoeff.H:9-41: xi, mu, lambda, Ddiag; no Soret): Y[n][N] -> D[n][N], mu[n], xi[n], lam[n]
+void
+peleref_transport(
+  int n, const double* T, const double* rho, const double* Y, double* D, double* mu, double* xi, double* lam)
+{
+  static pele::physics::PeleParams<pele::physics::transport::TransParm<
+    pele::physics::PhysicsType::eos_type, pele::physics::PhysicsType::transport_type>>
+    trans_parms;
+  static bool ready = false;
+  if (!ready) {
+    trans_parms.initialize();
+    ready = true;
+  }
+  auto const* tparm = trans_parms.device_parm();
+  auto trans = pele::physics::PhysicsType::transport();
+  for (int s = 0; s < n; ++s) {
+    Real yy[NUM_SPECIES], dd[NUM_SPECIES];
+    for (int k = 0; k < NUM_SPECIES; ++k) {
+      yy[k] = Y[s * NUM_SPECIES + k];
+    }
+    Real m = 0.0, x = 0.0, l = 0.0;
+    trans.transport(true, true, true, true, false, T[s], rho[s], yy, dd, nullptr, m, x, l, tparm);
+    for (int k = 0; k < NUM_SPECIES; ++k) {
+      D[s * NUM_SPECIES + k] = dd[k];
+    }
+    mu[s] = m;
+    xi[s] = x;
+    lam[s] = l;
   }
 }
 

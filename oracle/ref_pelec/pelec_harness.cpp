@@ -22,6 +22,7 @@
 
 #include "PeleC.H"
 #include "PeleCAmr.H"
+#include "Utilities.H"
 
 std::string inputs_name; // PC/Source/main.cpp:18 (IO.cpp writes it into job_info)
 
@@ -287,5 +288,50 @@ pelecref_react_state(int lev, double dt, int react_init, const double* aux)
   }
   l.react_state(pelecref_time(lev), dt, react_init != 0, react_init != 0 ? nullptr : &src);
 }
+
+// pc_ctoprim (PC/Source/Utilities.H:242-321) on n cells: u [NVAR][n] -> q [QVAR][n], qa [NQAUX][n].  Host build only.
+int
+pelecref_qvar()
+{
+  return QVAR;
+}
+
+int
+pelecref_nqaux()
+{
+  return NQAUX;
+}
+
+#ifndef AMREX_USE_GPU
+void
+pelecref_ctoprim(int n, const double* u, double* q, double* qa)
+{
+  const amrex::Box bx(amrex::IntVect(0, 0, 0), amrex::IntVect(n - 1, 0, 0));
+  amrex::FArrayBox ufab(bx, NVAR), qfab(bx, QVAR), qafab(bx, NQAUX);
+  auto const& ua = ufab.array();
+  auto const& qq = qfab.array();
+  auto const& qaa = qafab.array();
+  for (int c = 0; c < NVAR; ++c) {
+    for (int i = 0; i < n; ++i) {
+      ua(i, 0, 0, c) = u[static_cast<long>(c) * n + i];
+    }
+  }
+  qfab.setVal<amrex::RunOn::Host>(0.0);
+  qafab.setVal<amrex::RunOn::Host>(0.0);
+  for (int i = 0; i < n; ++i) {
+    pc_ctoprim(i, 0, 0, ufab.const_array(), qq, qaa);
+  }
+  for (int c = 0; c < QVAR; ++c) {
+    for (int i = 0; i < n; ++i) {
+      q[static_cast<long>(c) * n + i] = qq(i, 0, 0, c);
+    }
+  }
+  for (int c = 0; c < NQAUX; ++c) {
+    for (int i = 0; i < n; ++i) {
+      qa[static_cast<long>(c) * n + i] = qaa(i, 0, 0, c);
+    }
+  }
+}
+#endif
 
 } // extern "C"

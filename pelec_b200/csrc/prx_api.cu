@@ -711,6 +711,104 @@ int prx_compute_temp_boxes(
   return PRX_OK;
 }
 
+// ---- pc_ctoprim and SimpleTransport::get_transport_coeffs ------------------------------------------------
+static bool prim_box(const int* lo, const int* hi, int b, PrimArgs* a)
+{
+  long long nc = 1;
+  for (int d = 0; d < 3; d++) {
+    a->len[d] = hi[3 * b + d] - lo[3 * b + d] + 1;
+    nc *= a->len[d] > 0 ? a->len[d] : 0;
+  }
+  a->ncells = (nc > 2147483647LL) ? -1 : (int)nc;
+  return nc > 0;
+}
+
+int prx_ctoprim_boxes(
+  prx_handle* h, int nboxes, const int* lo, const int* hi, const prx_array4* u, const prx_array4* q, const prx_array4* qaux,
+  const prx_state_index* ix, const prx_prim_index* qx, double small_num, void* cuda_stream)
+{
+  if (h == nullptr || nboxes < 0 || ix == nullptr || qx == nullptr || (nboxes > 0 && (!lo || !hi || !u || !q || !qaux))) {
+    return PRX_ERR_BAD_ARG;
+  }
+  const int N = h->ops->num_species;
+  if (ix->nvar < ix->ufs + N || qx->qvar < qx->qfs + N || qx->nqaux < 6) {
+    return fail(h, PRX_ERR_BAD_ARG, "prx_ctoprim_boxes: index tables do not fit NUM_SPECIES");
+  }
+  DeviceGuard g(h->device);
+  NvtxRange nvtx("prx::ctoprim");
+  for (int b = 0; b < nboxes; b++) {
+    PrimArgs a;
+    std::memset(&a, 0, sizeof(a));
+    if (!prim_box(lo, hi, b, &a)) {
+      continue;
+    }
+    if (a.ncells < 0 || !view_of(u + b, lo + 3 * b, ix->nvar, &a.u, hi + 3 * b) || !view_of(q + b, lo + 3 * b, qx->qvar, &a.q, hi + 3 * b) ||
+        !view_of(qaux + b, lo + 3 * b, qx->nqaux, &a.qa, hi + 3 * b)) {
+      return fail(h, PRX_ERR_BAD_ARG, "prx_ctoprim_boxes: null/short Array4 or box outside the array");
+    }
+    a.ix.urho = ix->urho;
+    a.ix.umx = ix->umx;
+    a.ix.umy = ix->umy;
+    a.ix.umz = ix->umz;
+    a.ix.ueden = ix->ueden;
+    a.ix.ueint = ix->ueint;
+    a.ix.utemp = ix->utemp;
+    a.ix.ufs = ix->ufs;
+    a.qx.qrho = qx->qrho;
+    a.qx.qu = qx->qu;
+    a.qx.qv = qx->qv;
+    a.qx.qw = qx->qw;
+    a.qx.qgame = qx->qgame;
+    a.qx.qpres = qx->qpres;
+    a.qx.qreint = qx->qreint;
+    a.qx.qtemp = qx->qtemp;
+    a.qx.qfs = qx->qfs;
+    a.qx.qgamc = qx->qgamc;
+    a.qx.qc = qx->qc;
+    a.qx.qcsml = qx->qcsml;
+    a.qx.qdpdr = qx->qdpdr;
+    a.qx.qdpde = qx->qdpde;
+    a.qx.qrspec = qx->qrspec;
+    a.small_num = small_num;
+    const cudaError_t e = h->ops->ctoprim(a, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) {
+      return fail(h, PRX_ERR_CUDA, "ctoprim", e);
+    }
+  }
+  return PRX_OK;
+}
+
+int prx_transport_boxes(
+  prx_handle* h, int nboxes, const int* lo, const int* hi, const prx_array4* Y, const prx_array4* T, const prx_array4* rho,
+  const prx_array4* D, const prx_array4* mu, const prx_array4* xi, const prx_array4* lam, void* cuda_stream)
+{
+  if (h == nullptr || nboxes < 0 || (nboxes > 0 && (!lo || !hi || !Y || !T || !rho || !D || !mu || !xi || !lam))) {
+    return PRX_ERR_BAD_ARG;
+  }
+  const int N = h->ops->num_species;
+  DeviceGuard g(h->device);
+  NvtxRange nvtx("prx::get_transport_coeffs");
+  for (int b = 0; b < nboxes; b++) {
+    PrimArgs a;
+    std::memset(&a, 0, sizeof(a));
+    if (!prim_box(lo, hi, b, &a)) {
+      continue;
+    }
+    const int* l = lo + 3 * b;
+    const int* hh = hi + 3 * b;
+    if (a.ncells < 0 || !view_of(Y + b, l, N, &a.Y, hh) || !view_of(T + b, l, 1, &a.T, hh) || !view_of(rho + b, l, 1, &a.rho, hh) ||
+        !view_of(D + b, l, N, &a.D, hh) || !view_of(mu + b, l, 1, &a.mu, hh) || !view_of(xi + b, l, 1, &a.xi, hh) ||
+        !view_of(lam + b, l, 1, &a.lam, hh)) {
+      return fail(h, PRX_ERR_BAD_ARG, "prx_transport_boxes: null/short Array4 or box outside the array");
+    }
+    const cudaError_t e = h->ops->transport(a, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) {
+      return fail(h, PRX_ERR_CUDA, e == cudaErrorNotSupported ? "transport: no fit tables for this mechanism" : "transport", e);
+    }
+  }
+  return PRX_OK;
+}
+
 // ---- multi-box entry points: the MFIter loop of the caller (PC/Source/React.cpp:133-138) in one call ------------------
 // PeleC hands the reactor 16^3 - 64^3 boxes; a single small box cannot fill 148 SMs and its latency is the critical path of
 // its slowest cell.  The boxes of one call are independent, so they are issued round-robin on internal streams (as AMReX does

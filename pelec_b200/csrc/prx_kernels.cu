@@ -1909,6 +1909,222 @@ cudaError_t launch_compute_temp(const BoxArgs& a, cudaStream_t stream)
   return cudaGetLastError();
 }
 
+// ---- PeleC's conserved -> primitive conversion pc_ctoprim (PC/Source/Utilities.H:242-321) --------------
+// One thread per cell, grid-stride; every component row is a coalesced warp transaction along i.  Per cell: NVAR doubles
+// in, QVAR + NQAUX out (Fuego EOS: ideal-gas mixture, T from (e, Y) by the reference's Newton iteration).  Each EOS call is
+// restated in the reference's own association (RTY2Cs sums Y_k cv_k with CKCVMS, RTY2G / RTY2dpde_dpdre use CKCVBS).
+__global__ void PRX_CAT(ctoprim_kernel_, PRX_MECH_SUFFIX)(const PrimArgs a)
+{
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < a.ncells; c += gridDim.x * blockDim.x) {
+    const double* U = a.u.p + cell_offset(c, a.len, a.u.js, a.u.ks);
+    double* Q = a.q.p + cell_offset(c, a.len, a.q.js, a.q.ks);
+    double* QA = a.qa.p + cell_offset(c, a.len, a.qa.js, a.qa.ks);
+    const long long un = a.u.ns, qn = a.q.ns, an = a.qa.ns;
+    const double rho = __ldg(U + a.ix.urho * un);
+    const double rhoinv = 1.0 / rho;
+    const double vx = __ldg(U + a.ix.umx * un) * rhoinv;
+    const double vy = __ldg(U + a.ix.umy * un) * rhoinv;
+    const double vz = __ldg(U + a.ix.umz * un) * rhoinv;
+    const double kineng = 0.5 * rho * (vx * vx + vy * vy + vz * vz) - 0.5 * rho * 0.0 * 0.0 * 0.0 * 0.0; // omega = rad = 0
+    Q[a.qx.qrho * qn] = rho;
+    Q[a.qx.qu * qn] = vx;
+    Q[a.qx.qv * qn] = vy;
+    Q[a.qx.qw * qn] = vz;
+    double Y[N];
+    const double tiny = 1e-4 * 2.220446049250313e-16;
+#pragma unroll
+    for (int n = 0; n < N; n++) {
+      double y = __ldg(U + (a.ix.ufs + n) * un) / rho;
+      if (-tiny < y && y < tiny) {
+        y = 0.0;
+      }
+      Y[n] = y;
+      Q[(a.qx.qfs + n) * qn] = y;
+    }
+    const double e = (__ldg(U + a.ix.ueden * un) - kineng) * rhoinv;
+    double T = __ldg(U + a.ix.utemp * un);
+    double yow = 0.0; // Y2WBAR / CKMMWY / CKPY all accumulate Y_k * imw_k in species order
+#pragma unroll
+    for (int n = 0; n < N; n++) {
+      yow += Y[n] * prx_imw[n];
+    }
+    const double wbar = 1.0 / yow;
+    t_from_energy<1>(e, Y, T);
+    const double p = rho * PRX_RU * T * yow;          // CKPY
+    double cvms[N];
+    cv_R(cvms, T);                                    // CKCVMS = cv_R * (RU / mw_k literal)
+    double cv_s = 0.0;
+#pragma unroll
+    for (int n = 0; n < N; n++) {
+      cv_s += Y[n] * (cvms[n] * tr_ru_mw[n]);
+    }
+    const double g_s = (wbar * cv_s + PRX_RU) / (wbar * cv_s); // RTY2Cs
+    const double cs = sqrt(g_s * p / rho);
+    const double cvx = wbar * ckcvbs(T, Y);           // TY2G
+    const double gam1 = (cvx + PRX_RU) / cvx;
+    Q[a.qx.qtemp * qn] = T;
+    Q[a.qx.qreint * qn] = e * rho;
+    Q[a.qx.qpres * qn] = p;
+    Q[a.qx.qgame * qn] = p / (e * rho) + 1.0;
+    QA[a.qx.qdpdr * an] = p / rho;
+    QA[a.qx.qdpde * an] = (gam1 - 1.0) * rho;
+    QA[a.qx.qgamc * an] = gam1;
+    QA[a.qx.qc * an] = cs;
+    QA[a.qx.qcsml * an] = fmax(a.small_num, a.small_num * cs);
+    QA[a.qx.qrspec * an] = PRX_RU / wbar;
+  }
+}
+
+cudaError_t launch_ctoprim(const PrimArgs& a, cudaStream_t stream)
+{
+  if (a.ncells <= 0) {
+    return cudaSuccess;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long cap = (long long)sms * 8, want = ((long long)a.ncells + 255) / 256;
+  PRX_CAT(ctoprim_kernel_, PRX_MECH_SUFFIX)<<<(int)(want < cap ? want : cap), 256, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+// ---- SimpleTransport::get_transport_coeffs (PP/Source/Transport/Simple.H:230-447 with the Fuego EOS; PeleC's call site
+// PC/Source/Diffusion.cpp:182-222): mixture-averaged rho*D_k, shear viscosity mu, bulk viscosity xi, conductivity lambda from
+// (T, rho, Y) with the mechanism's log-T fits.  One thread per cell.  The binary-diffusion sum needs exp(-fit_ij(T)) for every
+// ordered species pair; the fit table is symmetric bit for bit (checked by the generator), so each unordered pair is
+// evaluated once and added to both species in the reference's own summation order (ascending partner index).
+#ifdef PRX_HAVE_TRANSPORT
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+__global__ void __launch_bounds__(128) PRX_CAT(transport_kernel_, PRX_MECH_SUFFIX)(const PrimArgs a)
+{
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < a.ncells; c += gridDim.x * blockDim.x) {
+    const double* Yp = a.Y.p + cell_offset(c, a.len, a.Y.js, a.Y.ks);
+    const double Tloc = a.T.p[cell_offset(c, a.len, a.T.js, a.T.ks)];
+    double Y[N], X[N];
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      Y[i] = __ldg(Yp + i * a.Y.ns);
+      sum += Y[i];
+    }
+    const double logT0 = log(Tloc), logT1 = logT0 * logT0, logT2 = logT0 * logT1;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      Y[i] += 1.e-15 * (sum / N - Y[i]);
+    }
+    double wbar = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      wbar += Y[i] * tr_iwt[i];
+    }
+    wbar = 1.0 / wbar;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      X[i] = Y[i] * wbar * tr_iwt[i];
+    }
+    // shear + bulk viscosity
+    double mu = 0.0, xi = 0.0;
+    {
+      double cvk[N];
+      cv_R(cvk, Tloc); // CKCVMS = cv_R * (RU / mw_k literal)
+      const double pi3_2 = pow(M_PI, 1.5);
+#pragma unroll 1
+      for (int i = 0; i < N; i++) {
+        double m = tr_fitmu[4 * i] + tr_fitmu[1 + 4 * i] * logT0 + tr_fitmu[2 + 4 * i] * logT1 + tr_fitmu[3 + 4 * i] * logT2;
+        m = exp(m);
+        mu += X[i] * (m * m * m * m * m * m);
+        const int nlin = tr_nlin[i];
+        if (nlin != 0) {
+          const double cvms = cvk[i] * tr_ru_mw[i];
+          const double cvkint = cvms * tr_wt[i] / PRX_RU - 1.50;
+          const double cvkrot = (nlin == 1) ? 1.0 : 1.5;
+          const double e298 = tr_eps[i] / 298.0, eT = tr_eps[i] / Tloc;
+          const double Fnorm = 1.0 + 0.50 * pi3_2 * sqrt(e298) + (2.0 + .50 * M_PI * M_PI) * e298 + pi3_2 * sqrt(e298) * e298;
+          const double FofT = 1.0 + 0.50 * pi3_2 * sqrt(eT) + (2.0 + .50 * M_PI * M_PI) * eT + pi3_2 * sqrt(eT) * eT;
+          const double xl = 0.250 * M_PI * (cvkint / (cvkint + 1.50) * cvkint / (cvkint + 1.50)) * tr_zrot[i] / cvkrot * Fnorm / FofT * m;
+          xi += X[i] * (sqrt(sqrt(xl * xl * xl)));
+        }
+      }
+      mu = cbrt(sqrt(mu));
+      xi = cbrt(xi * xi * xi * xi);
+    }
+    // conductivity
+    double lam = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < N; i++) {
+      double l = tr_fitlam[4 * i] + tr_fitlam[1 + 4 * i] * logT0 + tr_fitlam[2 + 4 * i] * logT1 + tr_fitlam[3 + 4 * i] * logT2;
+      l = exp(l);
+      lam += X[i] * sqrt(sqrt(l));
+    }
+    lam = lam * lam * lam * lam;
+    // mixture-averaged diffusion coefficients
+    double term2[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      term2[i] = 0.0;
+    }
+#if PRX_TR_DBIN_SYMMETRIC
+#pragma unroll 1
+    for (int i = 0; i < N; i++) {
+#pragma unroll 1
+      for (int j = i + 1; j < N; j++) {
+        const int f = 4 * (i + N * j);
+        const double d = tr_fitdbin[f] + tr_fitdbin[1 + f] * logT0 + tr_fitdbin[2 + f] * logT1 + tr_fitdbin[3 + f] * logT2;
+        const double ex = exp(-d);
+        term2[i] += X[j] * ex;
+        term2[j] += X[i] * ex;
+      }
+    }
+#else
+#pragma unroll 1
+    for (int i = 0; i < N; i++) {
+#pragma unroll 1
+      for (int j = 0; j < N; j++) {
+        if (i != j) {
+          const int f = 4 * (i + N * j);
+          const double d = tr_fitdbin[f] + tr_fitdbin[1 + f] * logT0 + tr_fitdbin[2 + f] * logT1 + tr_fitdbin[3 + f] * logT2;
+          term2[i] += X[j] * exp(-d);
+        }
+      }
+    }
+#endif
+    const double scale = 1.01325e+06 / (PRX_RU * Tloc); // Constants::PATM / (RU T)
+    double* Dp = a.D.p + cell_offset(c, a.len, a.D.js, a.D.ks);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      double term1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < N; j++) {
+        if (j != i) {
+          term1 += Y[j];
+        }
+      }
+      Dp[i * a.D.ns] = tr_wt[i] * term1 / term2[i] * scale;
+    }
+    a.mu.p[cell_offset(c, a.len, a.mu.js, a.mu.ks)] = mu;
+    a.xi.p[cell_offset(c, a.len, a.xi.js, a.xi.ks)] = xi;
+    a.lam.p[cell_offset(c, a.len, a.lam.js, a.lam.ks)] = lam;
+  }
+}
+
+cudaError_t launch_transport(const PrimArgs& a, cudaStream_t stream)
+{
+  if (a.ncells <= 0) {
+    return cudaSuccess;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long cap = (long long)sms * 16, want = ((long long)a.ncells + 127) / 128;
+  PRX_CAT(transport_kernel_, PRX_MECH_SUFFIX)<<<(int)(want < cap ? want : cap), 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+#else
+cudaError_t launch_transport(const PrimArgs&, cudaStream_t) { return cudaErrorNotSupported; }
+#endif
+
 cudaError_t launch_state_pack(const BoxArgs& a, cudaStream_t stream)
 {
   if (a.ncells <= 0) {
@@ -2154,7 +2370,8 @@ cudaError_t probe_jac(int n, int reactor_type, const double* y, double* J, cudaS
 int bdf_is_fused(const SchedParams& sp) { return effective_bdf_variant(sp) == 0; }
 
 const MechOps g_ops = {PRX_NUM_SPECIES, PRX_NUM_REACTIONS, PRX_MECH_NAME, prx_species_names, launch_rk64, launch_bdf, kernel_name, probe_rhs, probe_jac,
-                       launch_flatten, launch_unflatten, launch_state_pack, launch_state_unpack, bdf_is_fused, launch_compute_temp};
+                       launch_flatten, launch_unflatten, launch_state_pack, launch_state_unpack, bdf_is_fused, launch_compute_temp,
+                       launch_ctoprim, launch_transport};
 
 } // namespace
 

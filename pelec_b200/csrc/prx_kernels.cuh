@@ -54,6 +54,25 @@ struct BoxArgs
   const int* order; // optional: queue position -> cell index (cells sorted by temperature), nullptr = identity
 };
 
+// ---- pointwise EOS / transport kernels either side of the reactor ---------------------------------
+// primitive-state component indices (PC/Source/IndexDefines.H: QRHO ... QFS, QGAMC ... QRSPEC)
+struct PrimIx
+{
+  int qrho, qu, qv, qw, qgame, qpres, qreint, qtemp, qfs;
+  int qgamc, qc, qcsml, qdpdr, qdpde, qrspec;
+};
+struct PrimArgs
+{
+  int ncells;
+  int len[3];
+  ArrView u, q, qa;             // ctoprim: conserved state in, primitives + auxiliaries out
+  ArrView Y, T, rho;            // transport: inputs (component-offset views of q)
+  ArrView D, mu, xi, lam;       // transport: outputs (D: N components)
+  StateIx ix;
+  PrimIx qx;
+  double small_num;             // PeleC constants::small_num()
+};
+
 // device-side counters (unsigned long long so that atomicAdd applies)
 struct DevStats
 {
@@ -107,6 +126,8 @@ struct MechOps
   cudaError_t (*state_unpack)(const BoxArgs&, const prx_config&, cudaStream_t stream);
   int (*bdf_is_fused)(const SchedParams&); // 1: launch_bdf handles LAYOUT_STATE itself
   cudaError_t (*compute_temp)(const BoxArgs&, cudaStream_t stream); // pc_cmpTemp on a.snew
+  cudaError_t (*ctoprim)(const PrimArgs&, cudaStream_t stream);      // pc_ctoprim: u -> q, qa
+  cudaError_t (*transport)(const PrimArgs&, cudaStream_t stream);    // SimpleTransport::get_transport_coeffs
 };
 
 const MechOps* mech_ops_LiDryer();

@@ -720,6 +720,36 @@ class Emitter:
                 w("};")
         w()
 
+    # ------------------------------------------------------------------ Simple-transport fit tables
+    def emit_transport(self):
+        """The data TransParm<Fuego, SimpleTransport> holds (PP/Source/Transport/TransportParams.H:237-256): wt, iwt = 1 / wt,
+        eps, zrot, nlin, fitmu = COFETA, fitlam = COFLAM, fitdbin = COFD, as global-memory tables (fitdbin of dodecane_lu is
+        90 KB: no constant memory); the kernels index them with warp-uniform indices."""
+        t = self.d.get("transport")
+        w = self.w
+        if t is None:
+            return
+        N = self.N
+        assert t["NO"] == 4 and len(t["cofd"]) == 4 * N * N
+        cofd = [float(x) for x in t["cofd"]]
+        sym = all(cofd[4 * (i + N * j) + c] == cofd[4 * (j + N * i) + c] for i in range(N) for j in range(N) for c in range(4))
+        w("// ---- Simple transport (see Emitter.emit_transport) ----")
+        w("#define PRX_HAVE_TRANSPORT 1")
+        w("#define PRX_TR_DBIN_SYMMETRIC %d  // fitdbin(i,j) == fitdbin(j,i) bit for bit: one exponential per species pair" % (1 if sym else 0))
+        w("#define PRX_TR_PATM %s" % lit(t["patm"]))
+        for nm, ct, vals in (("wt", "double", [lit(x) for x in t["wt"]]),
+                             ("iwt", "double", [repr(1.0 / float(x)) for x in t["wt"]]),
+                             # RU / mw: the per-species literals of CKCVMS / CKCPMS (mechanism.H "multiply by R/molecularweight")
+                             ("ru_mw", "double", [lit(x) for x in t["ru_mw"]]),
+                             ("eps", "double", [lit(x) for x in t["eps"]]),
+                             ("zrot", "double", [lit(x) for x in t["zrot"]]),
+                             ("nlin", "int", [str(x) for x in t["nlin"]]),
+                             ("fitmu", "double", [lit(x) for x in t["cofeta"]]),
+                             ("fitlam", "double", [lit(x) for x in t["coflam"]]),
+                             ("fitdbin", "double", [lit(x) for x in t["cofd"]])):
+            w("PRX_TABG %s tr_%s[%d] = {%s};" % (ct, nm, len(vals), ", ".join(vals)))
+        w()
+
     # ------------------------------------------------------------------ whole file
     def emit(self):
         d = self.d
@@ -783,6 +813,7 @@ class Emitter:
             w("#undef log10")
             w("#endif")
         self.emit_tables()
+        self.emit_transport()
         w("#endif")
         return "\n".join(self.L) + "\n"
 

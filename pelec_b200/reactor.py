@@ -63,6 +63,12 @@ class prx_stats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
 
 
+class prx_prim_index(C.Structure):
+    """PC/Source/IndexDefines.H: primitive (QRHO ... QFS, QVAR) and auxiliary (QGAMC ... QRSPEC, NQAUX) component indices"""
+    _fields_ = [(n, C.c_int) for n in ("qrho", "qu", "qv", "qw", "qgame", "qpres", "qreint", "qtemp", "qfs", "qvar",
+                                       "qgamc", "qc", "qcsml", "qdpdr", "qdpde", "qrspec", "nqaux")]
+
+
 _lib = None
 
 
@@ -92,6 +98,8 @@ def load_library():
     L.prx_react_state_box.argtypes = [vp, ip, ip, a4, a4, a4, a4, a4, sx, C.c_double, C.c_int, vp]
     L.prx_react_state_boxes.argtypes = [vp, C.c_int, ip, ip, a4, a4, a4, a4, a4, sx, C.c_double, C.c_int, vp]
     L.prx_compute_temp_boxes.argtypes = [vp, C.c_int, ip, ip, a4, sx, vp]
+    L.prx_ctoprim_boxes.argtypes = [vp, C.c_int, ip, ip, a4, a4, a4, sx, C.POINTER(prx_prim_index), C.c_double, vp]
+    L.prx_transport_boxes.argtypes = [vp, C.c_int, ip, ip, a4, a4, a4, a4, a4, a4, a4, vp]
     L.prx_flatten.argtypes = [vp, ip, ip, C.c_int, C.c_int, a4, a4, a4, a4, a4, vp, vp, vp, vp, vp]
     L.prx_unflatten.argtypes = [vp, ip, ip, C.c_int, C.c_int, a4, a4, a4, a4, a4, vp, vp, vp, C.c_double, vp]
     L.prx_react_flat_host.argtypes = [vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int]
@@ -303,6 +311,38 @@ class ReactorB200:
         ix = ix or self.state_index(self.N)
         sp = C.c_void_p(stream) if stream else None
         self._check(self.lib.prx_compute_temp_boxes(self.h, nb, lo, hi, arr, C.byref(ix), sp))
+        return 0
+
+    # -- pc_ctoprim and SimpleTransport::get_transport_coeffs ---------------------------
+    @staticmethod
+    def prim_index(nspec):
+        """PeleC's layout with NUM_ADV = NUM_AUX = NUM_LIN = 0 (PC/Source/IndexDefines.H:15-30,71-78)"""
+        qx = prx_prim_index()
+        (qx.qrho, qx.qu, qx.qv, qx.qw, qx.qgame, qx.qpres, qx.qreint, qx.qtemp, qx.qfs) = range(9)
+        qx.qvar = 8 + nspec
+        (qx.qgamc, qx.qc, qx.qcsml, qx.qdpdr, qx.qdpde, qx.qrspec) = range(6)
+        qx.nqaux = 6
+        return qx
+
+    @staticmethod
+    def _boxes(boxes):
+        nb = len(boxes)
+        return nb, (C.c_int * (3 * nb))(*[v for b in boxes for v in b.lo]), (C.c_int * (3 * nb))(*[v for b in boxes for v in b.hi])
+
+    def ctoprim(self, boxes, u, q, qaux, ix=None, qx=None, small_num=1.0e-8, stream=None):
+        nb, lo, hi = self._boxes(boxes)
+        arrs = [(prx_array4 * nb)(*[a.c_struct() for a in lst]) for lst in (u, q, qaux)]
+        ix = ix or self.state_index(self.N)
+        qx = qx or self.prim_index(self.N)
+        sp = C.c_void_p(stream) if stream else None
+        self._check(self.lib.prx_ctoprim_boxes(self.h, nb, lo, hi, *arrs, C.byref(ix), C.byref(qx), float(small_num), sp))
+        return 0
+
+    def transport(self, boxes, Y, T, rho, D, mu, xi, lam, stream=None):
+        nb, lo, hi = self._boxes(boxes)
+        arrs = [(prx_array4 * nb)(*[a.c_struct() for a in lst]) for lst in (Y, T, rho, D, mu, xi, lam)]
+        sp = C.c_void_p(stream) if stream else None
+        self._check(self.lib.prx_transport_boxes(self.h, nb, lo, hi, *arrs, sp))
         return 0
 
     # -- flat react on device tensors ----------------------------------------------------------

@@ -299,6 +299,28 @@ def parse_reactions(src, nreac):
     return reactions
 
 
+def parse_transport(src, nsp):
+    """Simple-transport fit data: the literal tables of the egtranset* functions (PP/Source/Transport/TransportParams.H:128-176
+    copies them into TransParm: wt, eps, sig, dip, pol, zrot, nlin, fitmu = COFETA, fitlam = COFLAM, fitdbin = COFD)."""
+    def table(fn, count, integer=False):
+        body = func_body(src, "egtranset" + fn)
+        vals = [None] * count
+        for m in re.finditer(fn + r"\[(\d+)\] = (-?" + NUM + r");", body):
+            vals[int(m.group(1))] = int(m.group(2)) if integer else m.group(2)
+        assert None not in vals, fn
+        return vals
+    # RU / mw_k as CEPTR printed it (CKCVMS / CKCPMS "multiply by R/molecularweight"): not reproducible from the rounded mw
+    ru_mw = re.findall(r"cvms\[\d+\] \*= (" + NUM + r");", func_body(src, "CKCVMS"))
+    assert len(ru_mw) == nsp
+    no = int(re.search(r"\*NO = (\d+);", func_body(src, "egtransetNO")).group(1))
+    return {
+        "NO": no, "ru_mw": ru_mw, "patm": re.search(r"\*PATM = (" + NUM + r");", func_body(src, "egtransetPATM")).group(1),
+        "wt": table("WT", nsp), "eps": table("EPS", nsp), "sig": table("SIG", nsp), "dip": table("DIP", nsp),
+        "pol": table("POL", nsp), "zrot": table("ZROT", nsp), "nlin": table("NLIN", nsp, True),
+        "cofeta": table("COFETA", no * nsp), "coflam": table("COFLAM", no * nsp), "cofd": table("COFD", no * nsp * nsp),
+    }
+
+
 def extract(mech):
     src = open(os.path.join(MECH_DIR, mech, "mechanism.H")).read()
     nsp = int(re.search(r"#define NUM_GAS_SPECIES (\d+)", src).group(1))
@@ -339,6 +361,7 @@ def extract(mech):
         "T_newton": {"tmin": tmin, "tmax": tmax, "tol": "1.e-6", "maxiter": 200, "clamp": "100."},
         "thermo": thermo,
         "reactions": parse_reactions(src, nreac),
+        "transport": parse_transport(src, nsp),
     }
 
 
