@@ -433,7 +433,7 @@ def profile_states(mech, n):
     mw = np.array([float(x) for x in d["mw"]])
     imw = np.array([float(x) for x in d["imw"]])
     Ru = float(d["Ru"])
-    fuel = {"LiDryer": "H2", "drm19": "CH4", "dodecane_lu": "NC12H26"}[mech]
+    fuel = {"LiDryer": "H2", "drm19": "CH4", "dodecane_lu": "NC12H26", "BurkeDryer": "H2", "FFCM1_Red": "CH4"}[mech]
     X = np.zeros(N)
     X[names.index("O2")], X[names.index(fuel)], X[names.index("N2")] = 0.2, 0.1, 0.7
     Y = X * mw / (X * mw).sum()
@@ -615,7 +615,7 @@ def synth_states(mech, n):
     mw = np.array([float(x) for x in d["mw"]])
     imw = np.array([float(x) for x in d["imw"]])
     Ru = float(d["Ru"])
-    fuel = {"LiDryer": "H2", "drm19": "CH4", "dodecane_lu": "NC12H26"}[mech]
+    fuel = {"LiDryer": "H2", "drm19": "CH4", "dodecane_lu": "NC12H26", "BurkeDryer": "H2", "FFCM1_Red": "CH4"}[mech]
     X = np.zeros(N)
     X[names.index("O2")], X[names.index(fuel)], X[names.index("N2")] = 0.2, 0.1, 0.7
     Y = X * mw / (X * mw).sum()

@@ -129,6 +129,11 @@ PRX_API const char* prx_last_error(const prx_handle* h);
 PRX_API int prx_num_species(int mechanism);
 PRX_API int prx_num_reactions(int mechanism);
 PRX_API const char* prx_mechanism_name(int mechanism);
+/* Mechanisms beyond the three above: any mechanism of PP/Mechanisms the generator pipeline reproduces can be compiled in
+ * (pelec_b200/csrc/Makefile EXTRA_MECHS; ids 3, 4, ... in build order).  prx_mechanism_id: id by PelePhysics directory name,
+ * PRX_ERR_UNSUPPORTED if this build does not hold it. */
+PRX_API int prx_num_mechanisms(void);
+PRX_API int prx_mechanism_id(const char* name);
 PRX_API int prx_default_config(prx_config* cfg);
 
 /* ---- ReactorBase::react, Array4 version (ReactorBase.H:25-40) ----

@@ -16,7 +16,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 MECHS = ("LiDryer", "drm19", "dodecane_lu")
-FUEL = {"LiDryer": "H2", "drm19": "CH4", "dodecane_lu": "NC12H26"}
+FUEL = {"LiDryer": "H2", "drm19": "CH4", "dodecane_lu": "NC12H26", "BurkeDryer": "H2", "FFCM1_Red": "CH4"}
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)
 
@@ -336,7 +336,7 @@ def reacteval_states(lib, ncells_xyz, fuel=None):
     [-1,1]^3 (inputs.3d_Array4 geometry): T(y) = 2000 + 500*y/L + 100*sin(2*pi*y/(L/4)), P = 1 atm,
     X_fuel = 0.1, X_O2 = 0.2, X_N2 = 0.7; zero external sources; energy type 1 (rho*e)."""
     nx, ny, nz = ncells_xyz
-    fuel = fuel or FUEL[lib.mech]
+    fuel = fuel or FUEL.get(lib.mech) or next(f for f in ("NC12H26", "NC7H16", "C2H4", "CH4", "H2") if f in lib.species)
     X = np.zeros(lib.N)
     X[lib.species.index("O2")] = 0.2
     X[lib.species.index(fuel)] = 0.1

@@ -41,18 +41,18 @@ struct prx_handle
 
 namespace {
 
+// the mechanisms of this build in id order: LiDryer 0, drm19 1, dodecane_lu 2 (ABI constants), then the extra ones
+typedef const MechOps* (*MechFn)();
+#define PRX_MECH_X(name) mech_ops_##name,
+const MechFn g_mech_table[] = {
+#include "gen/mech_registry.inc"
+};
+#undef PRX_MECH_X
+constexpr int g_num_mechs = (int)(sizeof(g_mech_table) / sizeof(g_mech_table[0]));
+
 const MechOps* ops_for(int mech)
 {
-  switch (mech) {
-  case PRX_MECH_LIDRYER:
-    return mech_ops_LiDryer();
-  case PRX_MECH_DRM19:
-    return mech_ops_drm19();
-  case PRX_MECH_DODECANE_LU:
-    return mech_ops_dodecane_lu();
-  default:
-    return nullptr;
-  }
+  return (mech >= 0 && mech < g_num_mechs) ? g_mech_table[mech]() : nullptr;
 }
 
 int fail(prx_handle* h, int code, const char* what, cudaError_t ce = cudaSuccess)
@@ -1221,7 +1221,7 @@ int prx_react_flat_host(
 
 int prx_find_mechanism(int num_species, int num_reactions, const char* first_species, const char* last_species)
 {
-  for (int m = 0; m < 3; m++) {
+  for (int m = 0; m < g_num_mechs; m++) {
     const MechOps* o = ops_for(m);
     if (o == nullptr || o->num_species != num_species || o->num_reactions != num_reactions) {
       continue;
@@ -1233,6 +1233,18 @@ int prx_find_mechanism(int num_species, int num_reactions, const char* first_spe
       continue;
     }
     return m;
+  }
+  return PRX_ERR_UNSUPPORTED;
+}
+
+int prx_num_mechanisms() { return g_num_mechs; }
+
+int prx_mechanism_id(const char* name)
+{
+  for (int m = 0; name != nullptr && m < g_num_mechs; m++) {
+    if (std::strcmp(name, ops_for(m)->name) == 0) {
+      return m;
+    }
   }
   return PRX_ERR_UNSUPPORTED;
 }

@@ -130,9 +130,10 @@ struct MechOps
   cudaError_t (*transport)(const PrimArgs&, cudaStream_t stream);    // SimpleTransport::get_transport_coeffs
 };
 
-const MechOps* mech_ops_LiDryer();
-const MechOps* mech_ops_drm19();
-const MechOps* mech_ops_dodecane_lu();
+// one per kernel translation unit of this build (gen/mech_registry.inc, written by the Makefile from MECHS)
+#define PRX_MECH_X(name) const MechOps* mech_ops_##name();
+#include "gen/mech_registry.inc"
+#undef PRX_MECH_X
 
 } // namespace prx
 #endif

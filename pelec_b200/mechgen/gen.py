@@ -755,7 +755,7 @@ class Emitter:
         d = self.d
         N = self.N
         w = self.w
-        guard = "PRX_MECH_%s_GEN" % d["name"].upper()
+        guard = "PRX_MECH_%s_GEN" % d["name"].upper().replace("-", "_")
         w("// GENERATED by pelec_b200/mechgen/gen.py from pelec_b200/mechanisms/%s.json - do not edit." % d["name"])
         w("// flavour: %s" % self.fl)
         w("#ifndef %s" % guard)
@@ -888,7 +888,15 @@ def write_if_changed(path, text):
     return True
 
 
-def generate_all(repo_root, mechs=("LiDryer", "drm19", "dodecane_lu")):
+def shipped_mechanisms():
+    """the three BASELINE mechanisms first (ABI ids 0-2), then every other pelec_b200/mechanisms/<mech>.json"""
+    core = ["LiDryer", "drm19", "dodecane_lu"]
+    extra = sorted(f[:-5] for f in os.listdir(MECH_JSON_DIR) if f.endswith(".json") and f[:-5] not in core)
+    return tuple(core + extra)
+
+
+def generate_all(repo_root, mechs=None):
+    mechs = mechs or shipped_mechanisms()
     out = []
     for m in mechs:
         p = os.path.join(repo_root, "oracle", "gen", "mech_%s.h" % m)
@@ -904,13 +912,17 @@ def generate_all(repo_root, mechs=("LiDryer", "drm19", "dodecane_lu")):
             text = constify(text)
         write_if_changed(p, text)
         out.append(p)
+        # build settings: a mechanism without its own entries in pelec_b200/csrc/Makefile takes those of the nearest of the three
+        n = len(load(m)["species"])
+        cls = m if m in ("LiDryer", "drm19", "dodecane_lu") else ("LiDryer" if n <= 14 else "drm19" if n <= 32 else "dodecane_lu")
+        write_if_changed(os.path.join(repo_root, "pelec_b200", "csrc", "gen", "mech_%s.mk" % m), "CLASS_%s := %s\n" % (m, cls))
     return out
 
 
 if __name__ == "__main__":
     import sys
     root = os.path.abspath(os.path.join(HERE, "..", ".."))
-    for p in generate_all(root, tuple(sys.argv[1:]) or ("LiDryer", "drm19", "dodecane_lu")):
+    for p in generate_all(root, tuple(sys.argv[1:]) or None):
         print(os.path.relpath(p, root), os.path.getsize(p), "bytes")
 
 

@@ -178,8 +178,14 @@ class ReactorB200:
         return cls(key, mechanism, **parm)
 
     def __init__(self, key, mechanism, **parm):
-        if mechanism not in MECHANISMS:
-            raise KeyError("Unknown mechanism '%s'. Valid: %s" % (mechanism, ", ".join(MECHANISMS)))
+        if mechanism not in MECHANISMS:  # a mechanism beyond the three ABI constants: ask the library of this build
+            lib = load_library()
+            lib.prx_mechanism_id.argtypes = [C.c_char_p]
+            mid = lib.prx_mechanism_id(mechanism.encode())
+            if mid < 0:
+                valid = [lib.prx_mechanism_name(i).decode() for i in range(lib.prx_num_mechanisms())]
+                raise KeyError("Unknown mechanism '%s'. This build holds: %s" % (mechanism, ", ".join(valid)))
+            MECHANISMS[mechanism] = mid
         self.key = key
         self.mechanism = mechanism
         # ParmParse-style keys with the reference's defaults (ReactorCvode.cpp:18-35, ReactorRK64.cpp:12-18)

@@ -158,15 +158,20 @@ def parse_fcent(stmt):
     arg = m.group(1).strip()
     terms = []
     pos = 0
-    pat_e = re.compile(r"\s*([+-])?\s*(" + NUM + r") \* exp\(-T \* (" + NUM + r")\)")
+    # CEPTR prints every Troe term; absent ones appear as a literal 0.0 (dropping "+ 0.0" is exact), negative coefficients as
+    # "+ -0.569 * exp(...)", the leading one sometimes in parentheses
+    pat_e = re.compile(r"\s*([+-])?\s*\(?(-?" + NUM + r")\)? \* exp\(-T \* (-?" + NUM + r")\)")
     pat_t2 = re.compile(r"\s*\+\s*exp\((-?" + NUM + r") \* invT\)")
-    pat_c = re.compile(r"\s*\+\s*(" + NUM + r")\s*$")
+    pat_c = re.compile(r"\s*\+?\s*(" + NUM + r")\s*(?=\+|$)")
     t2 = None
     const = None
     while pos < len(arg):
         m = pat_e.match(arg, pos)
         if m:
-            terms.append([("-" if m.group(1) == "-" else "") + m.group(2), m.group(3)])
+            coef = m.group(2)
+            if m.group(1) == "-":
+                coef = coef[1:] if coef.startswith("-") else "-" + coef
+            terms.append([coef, m.group(3)])
             pos = m.end()
             continue
         m = pat_t2.match(arg, pos)
@@ -176,7 +181,10 @@ def parse_fcent(stmt):
             continue
         m = pat_c.match(arg, pos)
         if m:
-            const = m.group(1)
+            if m.end() == len(arg) or float(m.group(1)) != 0.0:  # the trailing constant is kept as printed, even 0.0
+                if const is not None and float(const) != 0.0:
+                    raise ValueError("Fcent: two constants in %r" % arg)
+                const = m.group(1)
             pos = m.end()
             continue
         raise ValueError("Fcent: %r" % arg[pos:])
@@ -345,6 +353,8 @@ def extract(mech):
     ckrp = func_body(src, "CKRP")
     ru = re.search(r"ru = (" + NUM + r");", ckrp).group(1)
     prod = func_body(src, "productionRate")
+    if "pow(" in prod:
+        raise NotImplementedError("global reactions with non-integer orders (pow in productionRate) are not represented")
     refc = re.search(r"refC = (" + NUM + r") / (" + NUM + r") \* invT;", prod)
     tmin = re.search(r"tmin = (" + NUM + r");", func_body(src, "GET_T_GIVEN_EY")).group(1)
     tmax = re.search(r"tmax = (" + NUM + r");", func_body(src, "GET_T_GIVEN_EY")).group(1)
@@ -370,7 +380,7 @@ def main():
     os.makedirs(outdir, exist_ok=True)
     for mech in sys.argv[1:] or ["LiDryer", "drm19", "dodecane_lu"]:
         d = extract(mech)
-        path = os.path.join(outdir, mech + ".json")
+        path = os.path.join(outdir, mech.replace("-", "_") + ".json")  # file / C identifier; "name" keeps the directory name
         with open(path, "w") as f:
             json.dump(d, f, indent=0, separators=(",", ":"))
         kinds = {}
