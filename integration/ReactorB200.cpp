@@ -123,8 +123,19 @@ int ReactorB200<KIND>::init(int reactor_type, int /*ncells*/)
       cfg.solve_type = PRX_SOLVE_DENSE_AJ_DIRECT;
     } else if (solve_type_str == "dense_direct") {
       cfg.solve_type = PRX_SOLVE_DENSE_DIRECT;
+    } else if (
+      solve_type_str == "GMRES" || solve_type_str == "precGMRES" || solve_type_str == "sparse_direct" ||
+      solve_type_str == "custom_direct" || solve_type_str == "magma_direct") {
+      // The other linear solvers of the reference (ReactorCvode.cpp:527-647) are different ways of solving the SAME Newton
+      // systems (matrix-free Krylov, sparse / batched direct): an input file written for them keeps working - every cell's
+      // system is solved with a dense LU of the analytic Jacobian, the answer agrees within the integrator tolerance
+      // (tests/test_pelec_dropin.py runs the shipped pmf-lidryer-cvode.inp, solve_type = GMRES, unchanged); linear-solver
+      // iteration counts and nfeLS are not reproduced.
+      amrex::Print() << "ReactorCvodeB200: cvode.solve_type = " << solve_type_str
+                     << " -> per-cell dense LU of the analytic Jacobian (denseAJ_direct)\n";
+      cfg.solve_type = PRX_SOLVE_DENSE_AJ_DIRECT;
     } else {
-      amrex::Abort("ReactorCvodeB200: cvode.solve_type must be denseAJ_direct or dense_direct (got " + solve_type_str + ")");
+      amrex::Abort("ReactorCvodeB200: unknown cvode.solve_type " + solve_type_str);
     }
   }
 #ifdef AMREX_USE_GPU

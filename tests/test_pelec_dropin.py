@@ -71,3 +71,25 @@ def test_pmf_with_b200_reactor_matches_stock_pelec(stock, stock_cuda, ours, ours
     print("PMF %s%s vs %s%s after %d coarse steps: worst relative difference of the state %.2e (%s), of the heat release %.2e; wall %.1f s vs %.1f s" % (
         stock, " (CUDA build)" if stock_cuda else "", ours, " (CUDA build)" if ours_cuda else "", NSTEPS, max(worst.values()), max(worst, key=worst.get), hr_worst, float(a["wall_s"]), float(b["wall_s"])))
     assert max(worst.values()) <= tol, worst
+
+
+@pytest.mark.skipif(not os.path.exists(LIB), reason="oracle/_ref/libpelec_pmf_LiDryer.so not built")
+def test_shipped_pmf_input_with_only_the_integrator_key_changed(tmp_path):
+    """The shipped pmf-lidryer-cvode.inp (cvode.solve_type = GMRES, default tolerances) with pelec.chem_integrator as the ONLY
+    change, plus the two PeleC options that feed the reactor: typical values (PeleC::set_typical_values_chem,
+    PC/Source/React.cpp:8-27 -> ReactorBase::set_typ_vals_ode) and the reaction work estimate (React.cpp:316-322).  The stock run
+    solves every cell's Newton systems with matrix-free GMRES, the B200 reactor with a dense LU: same BDF, answers within the
+    integrator's tolerance (rtol 1e-6)."""
+    extra = ["cvode.solve_type=GMRES", "pelec.use_typ_vals_chem=1", "amr.loadbalance_with_workestimates=1"]
+    a = run("ReactorCvode", tmp_path, extra)
+    b = run("ReactorCvodeB200", tmp_path, extra)
+    assert a["finest"] == b["finest"] >= 1 and a["time"] == b["time"]
+    worst = 0.0
+    for lev in range(int(a["finest"]) + 1):
+        assert np.array_equal(a["boxes%d" % lev], b["boxes%d" % lev])
+        sa, sb = a["S%d" % lev], b["S%d" % lev]
+        for c in range(sa.shape[0]):
+            scale = max(np.abs(sa[c]).max(), 1e-6 * np.abs(sa[0]).max() if c >= 7 else 0.0, np.abs(sa[3]).max() if c in (1, 2) else 0.0)
+            worst = max(worst, float(np.abs(sa[c] - sb[c]).max() / scale))
+    print("PMF, shipped input (GMRES, typical values, load balance): worst relative difference of the state %.2e" % worst)
+    assert worst <= 1e-5

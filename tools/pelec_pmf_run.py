@@ -35,7 +35,10 @@ def main():
     args = ["pelec", os.path.join(case, "pmf-lidryer-cvode.inp"), "amr.plot_files_output=0", "amr.checkpoint_files_output=0",
             "pelec.xNormPlane.int=100000", "prob.pmf_datafile=" + os.path.join(case, "LiDryer_H2_p1_phi0_4000tu0300.dat"),
             "pelec.v=0", "amr.v=0", "pelec.sum_interval=-1", "pelec.chem_integrator=" + integ,
-            "cvode.solve_type=denseAJ_direct", "ode.analytical_jacobian=1", "ode.clean_init_massfrac=0"] + extra
+            "ode.clean_init_massfrac=0"]
+    if not any(e.startswith("cvode.solve_type=") for e in extra):  # default of these runs; "cvode.solve_type=GMRES" = the shipped input
+        args += ["cvode.solve_type=denseAJ_direct", "ode.analytical_jacobian=1"]
+    args += extra
     argv = (C.c_char_p * len(args))(*[a.encode() for a in args])
     lib.pelecref_init.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
     lib.pelecref_ncells.restype = C.c_long
