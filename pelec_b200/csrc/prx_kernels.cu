@@ -1913,7 +1913,7 @@ cudaError_t launch_compute_temp(const BoxArgs& a, cudaStream_t stream)
 // One thread per cell, grid-stride; every component row is a coalesced warp transaction along i.  Per cell: NVAR doubles
 // in, QVAR + NQAUX out (Fuego EOS: ideal-gas mixture, T from (e, Y) by the reference's Newton iteration).  Each EOS call is
 // restated in the reference's own association (RTY2Cs sums Y_k cv_k with CKCVMS, RTY2G / RTY2dpde_dpdre use CKCVBS).
-__global__ void PRX_CAT(ctoprim_kernel_, PRX_MECH_SUFFIX)(const PrimArgs a)
+__global__ void __launch_bounds__(256, (PRX_NUM_SPECIES <= 16) ? 4 : 2) PRX_CAT(ctoprim_kernel_, PRX_MECH_SUFFIX)(const PrimArgs a)
 {
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < a.ncells; c += gridDim.x * blockDim.x) {
     const double* U = a.u.p + cell_offset(c, a.len, a.u.js, a.u.ks);
@@ -2065,10 +2065,15 @@ __global__ void __launch_bounds__(128) PRX_CAT(transport_kernel_, PRX_MECH_SUFFI
     for (int i = 0; i < N; i++) {
       term2[i] = 0.0;
     }
+#if PRX_NUM_SPECIES <= 16
+#define PRX_TR_PAIR_UNROLL _Pragma("unroll") // small mechanisms: the pair loops unroll, term2[] stays in registers
+#else
+#define PRX_TR_PAIR_UNROLL _Pragma("unroll 1")
+#endif
 #if PRX_TR_DBIN_SYMMETRIC
-#pragma unroll 1
+    PRX_TR_PAIR_UNROLL
     for (int i = 0; i < N; i++) {
-#pragma unroll 1
+      PRX_TR_PAIR_UNROLL
       for (int j = i + 1; j < N; j++) {
         const int f = 4 * (i + N * j);
         const double d = tr_fitdbin[f] + tr_fitdbin[1 + f] * logT0 + tr_fitdbin[2 + f] * logT1 + tr_fitdbin[3 + f] * logT2;
