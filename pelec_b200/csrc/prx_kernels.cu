@@ -44,6 +44,9 @@
 #ifndef PRX_PREFETCH_SRC
 #define PRX_PREFETCH_SRC 0
 #endif
+#ifndef PRX_PREFETCH_STATE
+#define PRX_PREFETCH_STATE 0
+#endif
 #ifndef PRX_BDF_DEFAULT_VARIANT
 #define PRX_BDF_DEFAULT_VARIANT 0
 #endif
@@ -601,6 +604,42 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
       for (int k = 0; k < N; k++) {
         asm volatile("prefetch.L1 [%0];" ::"l"(&s.src.rYsrc[k]));
       }
+#endif
+#if PRX_PREFETCH_STATE
+      // The control phase that follows the RHS reads the Newton matrix (triangular solves) and the hot vectors from local
+      // memory that has left L1 / L2 while 20 other warps ran (ncu r02i: L1 hit 41 %, L2 hit 51 %, long-scoreboard 41 % of the
+      // stall samples): start those fetches now, behind ~5 k instructions of register-only chemistry.  MEASURED (r02y, 128^3
+      // LiDryer): 67.4 ms without, 71.7 ms with the matrix prefetched (L1 or L2), 74.1 ms with matrix + vectors - the kernel's
+      // memory system is saturated by the state traffic itself, extra requests only queue.  OFF.  Local memory interleaves
+      // the lanes of a warp by 32-bit word, so a double is two 128-byte rows.  Bit 0: the matrix, bit 1: zn0, zn1, acor, ewt,
+      // tempv; bit 2: into L1 instead of L2.
+#define PRX_PF(ptr)                                                                         \
+  do {                                                                                      \
+    if (PRX_PREFETCH_STATE & 4) {                                                           \
+      asm volatile("prefetch.L1 [%0];" ::"l"(ptr));                                         \
+      asm volatile("prefetch.L1 [%0];" ::"l"(reinterpret_cast<const char*>(ptr) + 4));      \
+    } else {                                                                                \
+      asm volatile("prefetch.L2 [%0];" ::"l"(ptr));                                         \
+      asm volatile("prefetch.L2 [%0];" ::"l"(reinterpret_cast<const char*>(ptr) + 4));      \
+    }                                                                                       \
+  } while (0)
+      if (PRX_PREFETCH_STATE & 1) {
+#pragma unroll
+        for (int k = 0; k < NEQ * NEQ; k++) {
+          PRX_PF(&s.A_[k]);
+        }
+      }
+      if (PRX_PREFETCH_STATE & 2) {
+#pragma unroll
+        for (int k = 0; k < NEQ; k++) {
+          PRX_PF(&s.zn_[0][k]);
+          PRX_PF(&s.zn_[1][k]);
+          PRX_PF(&s.acor_[k]);
+          PRX_PF(&s.ewt_[k]);
+          PRX_PF(&s.tempv_[k]);
+        }
+      }
+#undef PRX_PF
 #endif
 #if PRX_OUTLINE & 2
       rhs_outline(s.t_eval, p.reactor_type, s.vec(s.in_sel), s.vec(s.out_sel), &s.src);
@@ -2065,11 +2104,9 @@ __global__ void __launch_bounds__(128) PRX_CAT(transport_kernel_, PRX_MECH_SUFFI
     for (int i = 0; i < N; i++) {
       term2[i] = 0.0;
     }
-#if PRX_NUM_SPECIES <= 16
-#define PRX_TR_PAIR_UNROLL _Pragma("unroll") // small mechanisms: the pair loops unroll, term2[] stays in registers
-#else
+// rolled pair loops (term2[] in L1-resident local memory): unrolling them for small mechanisms was measured slower
+// (r02y, 192^3 LiDryer: 2.48 vs 2.37 ms)
 #define PRX_TR_PAIR_UNROLL _Pragma("unroll 1")
-#endif
 #if PRX_TR_DBIN_SYMMETRIC
     PRX_TR_PAIR_UNROLL
     for (int i = 0; i < N; i++) {

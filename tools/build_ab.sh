@@ -11,6 +11,6 @@ mkdir -p ../lib/obj_$TAG
 nvcc $NVF -DPRX_MECH_HEADER="\"$H\"" -DPRX_MECH_SUFFIX=LiDryer -DPRX_BLOCK=${LB:-224} -DPRX_MINBLOCKS=${LM:-3} -DPRX_RK_BLOCK=${RB:-256} -DPRX_RK_MINBLOCKS=${RM:-2} -DPRX_COOP_BLOCK_WARPS=1 "$@" -c prx_kernels.cu -o ../lib/obj_$TAG/kernels_LiDryer.o 2> ../lib/obj_$TAG/kernels_LiDryer.log
 grep -i "error" -A3 ../lib/obj_$TAG/*.log | head
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../lib/libpelerx_b200_$TAG.so ../lib/obj/api.o ../lib/obj_$TAG/kernels_LiDryer.o \
-   ../lib/obj/kernels_drm19.o ../lib/obj/kernels_dodecane_lu.o -Xlinker --version-script=exports.map -lcudart
+   $(ls ../lib/obj/kernels_*.o | grep -v kernels_LiDryer.o) -Xlinker --version-script=exports.map -lcudart
 ls -la ../lib/libpelerx_b200_$TAG.so
 grep -h -A2 "18bdf_kernel\|rk64_kernel" ../lib/obj_$TAG/kernels_*.log | grep "Used\|stack"
