@@ -18,6 +18,7 @@
 // HBM traffic is only the boundary arrays: (2N+3) doubles in, (N+3) out per cell.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "prx_integrators.cuh"
 #include "prx_tchem.cuh"
@@ -1203,14 +1204,28 @@ struct SrcScal
 };
 
 #define PRX_HAVE_BDF4 (PRX_FULL_VARIANTS && PRX_NUM_SPECIES <= 12)
-#if PRX_HAVE_BDF4
-template <int NT>
-__global__ void __launch_bounds__(NT, 1) PRX_CAT(bdf4_kernel_, PRX_MECH_SUFFIX)(
-  const BoxArgs a, const BdfParams p, const SchedParams sp, int* __restrict__ queue, DevStats* __restrict__ stats)
+// Variant 6 (round 2, session r02z): the same kernel body with the block shape of the first generation (PRX_BLOCK x
+// PRX_MINBLOCKS, straight-line chemistry, Newton matrix and saved Jacobian thread-local) and the VECTORS of the integrator
+// (Nordsieck array, ewt, acor, tempv, ftemp, y, delta, species source) as coalesced columns of a GLOBAL buffer that is pinned
+// in L2 by an access-policy window (persisting lines, cudaLimitPersistingL2CacheSize): the vectors are what every step and
+// every Newton iteration re-reads and re-writes after 20 other warps have flushed them out of an LRU L2; local memory cannot
+// carry an access policy, an explicit buffer can.  No occupancy is traded for it.
+// MEASURED (r02z, 128^3 LiDryer): 67.5 ms (first generation), 78.1 ms with the vectors in the global buffer, 83.8 ms with the
+// buffer pinned in L2 (PRX_L2_PERSIST=1): the persisting carve-out takes the L2 away from the Newton matrix, the saved
+// Jacobian and the spills, which lose more than the vectors gain.  A dead end like variants 1-5: built only with
+// -DPRX_FULL_VARIANTS=1.
+#ifndef PRX_HAVE_BDF6
+#define PRX_HAVE_BDF6 (PRX_FULL_VARIANTS && PRX_NUM_SPECIES <= 24 && !defined(PRX_AUDIT_RK64_ONLY))
+#endif
+#if PRX_HAVE_BDF4 || PRX_HAVE_BDF6
+template <int NT, bool A_SMEM, int MINB, bool GLOBAL>
+__global__ void __launch_bounds__(NT, MINB) PRX_CAT(bdf4_kernel_, PRX_MECH_SUFFIX)(
+  const BoxArgs a, const BdfParams p, const SchedParams sp, int* __restrict__ queue, DevStats* __restrict__ stats,
+  double* __restrict__ gbuf, const int doubles_per_thread)
 {
-  typedef BdfCellT<BdfStoreSmem<NT, true>, SrcScal> Cell;
+  typedef BdfCellT<BdfStoreSmem<NT, A_SMEM>, SrcScal> Cell;
   Cell s;
-  s.base = prx_dyn_smem + threadIdx.x;
+  s.base = GLOBAL ? (gbuf + (size_t)blockIdx.x * NT * (size_t)doubles_per_thread + threadIdx.x) : (prx_dyn_smem + threadIdx.x);
   s.nz = p.qmax + 1;
   int cell = -1;
   bool exhausted = false;
@@ -1280,7 +1295,7 @@ __global__ void __launch_bounds__(NT, 1) PRX_CAT(bdf4_kernel_, PRX_MECH_SUFFIX)(
         req = REQ_NONE;
       }
       if (req == REQ_LU) {
-        s.lu_info = dense_getrf_small(s.A(), s.piv(), s.perm());
+        s.lu_info = (NEQ <= 12) ? dense_getrf_small(s.A(), s.piv(), s.perm()) : ((NEQ <= 24) ? dense_getrf_mid(s.A(), s.piv(), s.perm()) : dense_getrf(s.A(), s.piv()));
         req = REQ_NONE;
       }
     }
@@ -1336,11 +1351,81 @@ __global__ void __launch_bounds__(NT, 1) PRX_CAT(bdf4_kernel_, PRX_MECH_SUFFIX)(
   flush_stats(ls, stats);
 }
 
+#endif // PRX_HAVE_BDF4 || PRX_HAVE_BDF6
+
+#if PRX_HAVE_BDF6
+cudaError_t launch_bdf6(const BoxArgs& a, const BdfParams& p, const SchedParams& sp, int* queue, DevStats* stats, cudaStream_t stream)
+{
+  constexpr int NT = PRX_BLOCK;
+  typedef BdfStoreSmem<NT, false> Store;
+  auto kern = PRX_CAT(bdf4_kernel_, PRX_MECH_SUFFIX)<NT, false, PRX_MINBLOCKS, true>;
+  int dev = 0, sms = 148, per_sm = 0, max_persist = 0, max_window = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+  cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, 0) != cudaSuccess || per_sm < 1) {
+    return cudaErrorInvalidConfiguration;
+  }
+  long long grid = (long long)sms * per_sm;
+  const long long needed = ((long long)a.ncells + NT - 1) / NT;
+  grid = needed < grid ? needed : grid;
+  const int dpt = Store::doubles_per_thread(p.qmax);
+  const size_t bytes = sizeof(double) * (size_t)grid * NT * (size_t)dpt;
+  double* gbuf = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&gbuf, bytes, stream);
+  if (e != cudaSuccess) {
+    return e;
+  }
+  // pin the buffer in L2: persisting carve-out as large as the device allows, hit ratio scaled when the buffer is larger
+  static const bool want_persist = [] {
+    const char* ev = std::getenv("PRX_L2_PERSIST");
+    return ev == nullptr || ev[0] != '0';
+  }();
+  bool window_set = false;
+  if (want_persist && max_persist > 0 && max_window > 0) {
+    static int carved_dev = -1;
+    if (carved_dev != dev) {
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+      carved_dev = dev;
+    }
+    cudaStreamAttrValue av;
+    std::memset(&av, 0, sizeof(av));
+    const size_t win = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+    av.accessPolicyWindow.base_ptr = gbuf;
+    av.accessPolicyWindow.num_bytes = win;
+    const double ratio = (double)max_persist / (double)win;
+    av.accessPolicyWindow.hitRatio = ratio >= 1.0 ? 1.0f : (float)ratio;
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    window_set = (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess);
+    if (!window_set) {
+      cudaGetLastError();
+    }
+  }
+  e = cudaMemsetAsync(queue, 0, sizeof(int), stream);
+  if (e == cudaSuccess) {
+    kern<<<(int)grid, NT, 0, stream>>>(a, p, sp, queue, stats, gbuf, dpt);
+    e = cudaGetLastError();
+  }
+  if (window_set) { // the window belongs to this launch only: give the caller's stream back as it was
+    cudaStreamAttrValue av;
+    std::memset(&av, 0, sizeof(av));
+    av.accessPolicyWindow.num_bytes = 0;
+    cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av);
+  }
+  cudaFreeAsync(gbuf, stream);
+  return e;
+}
+#endif
+
+#if PRX_HAVE_BDF4
 template <int NT>
 cudaError_t launch_bdf4_nt(const BoxArgs& a, const BdfParams& p, const SchedParams& sp, int* queue, DevStats* stats, cudaStream_t stream)
 {
   typedef BdfStoreSmem<NT, true> Store;
-  auto kern = PRX_CAT(bdf4_kernel_, PRX_MECH_SUFFIX)<NT>;
+  auto kern = PRX_CAT(bdf4_kernel_, PRX_MECH_SUFFIX)<NT, true, 1, false>;
   const size_t smem = sizeof(double) * NT * (size_t)Store::doubles_per_thread(p.qmax);
   int dev = 0, sms = 148, per_sm = 0;
   cudaGetDevice(&dev);
@@ -1360,7 +1445,7 @@ cudaError_t launch_bdf4_nt(const BoxArgs& a, const BdfParams& p, const SchedPara
   if (e != cudaSuccess) {
     return e;
   }
-  kern<<<(int)grid, NT, smem, stream>>>(a, p, sp, queue, stats);
+  kern<<<(int)grid, NT, smem, stream>>>(a, p, sp, queue, stats, nullptr, 0);
   return cudaGetLastError();
 }
 
@@ -2300,6 +2385,11 @@ cudaError_t launch_bdf(
     return launch_bdf3<true>(a, p, sp, queue, stats, stream);
   }
 #endif
+#if PRX_HAVE_BDF6
+  if (variant == 6 && a.layout != LAYOUT_STATE) {
+    return launch_bdf6(a, p, sp, queue, stats, stream);
+  }
+#endif
 #if PRX_HAVE_BDF4
   if (variant == 5) {
     return launch_bdf4(a, p, sp, queue, stats, stream);
@@ -2355,6 +2445,11 @@ int effective_bdf_variant(const SchedParams& sp)
 #else
   (void)0;
 #endif
+#if !PRX_HAVE_BDF6
+  if (v == 6) {
+    v = 0;
+  }
+#endif
 #if !PRX_HAVE_BDF1
   if (v == 0) {
     v = 32;
@@ -2380,6 +2475,7 @@ const char* kernel_name(int reactor_kind, const SchedParams& sp)
   case 4:
     return "bdf3_kernel_" PRX_STR(PRX_MECH_SUFFIX);
   case 5:
+  case 6:
     return "bdf4_kernel_" PRX_STR(PRX_MECH_SUFFIX);
   default:
     return "bdf_kernel_" PRX_STR(PRX_MECH_SUFFIX);

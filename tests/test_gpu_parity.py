@@ -299,7 +299,7 @@ def test_flatten_unflatten_match_reference_semantics(ordering):
     r.close()
 
 
-BDF_VARIANTS = {"LiDryer": (0, 1, 2, 3, 4, 5, 8, 16, 32), "drm19": (0, 2, 3, 8, 16, 32), "dodecane_lu": (32,)}
+BDF_VARIANTS = {"LiDryer": (0, 1, 2, 3, 4, 5, 6, 8, 16, 32), "drm19": (0, 2, 3, 6, 8, 16, 32), "dodecane_lu": (32,)}
 
 
 @pytest.mark.parametrize("variant", sorted({v for vs in BDF_VARIANTS.values() for v in vs}))
@@ -315,10 +315,10 @@ def test_every_bdf_kernel_generation_matches_golden(mech, variant, monkeypatch):
     kw = CVODE_SETTINGS[0]
     r = make_reactor("ReactorCvode", mech, **cvode_parm(kw))
     name = r.kernel_name()
-    want = {0: "bdf_kernel_", 1: "bdf2_", 2: "bdf2_", 3: "bdf3_", 4: "bdf3_", 5: "bdf4_"}.get(variant, "bdfc_kernel_")[:4]
-    if variant in (1, 2, 3, 4, 5) and not name.startswith(want):
+    want = {0: "bdf_kernel_", 1: "bdf2_", 2: "bdf2_", 3: "bdf3_", 4: "bdf3_", 5: "bdf4_", 6: "bdf4_"}.get(variant, "bdfc_kernel_")[:4]
+    if variant in (1, 2, 3, 4, 5, 6) and not name.startswith(want):
         r.close()
-        pytest.skip("storage variants 1-5 are measured dead ends, built only with -DPRX_FULL_VARIANTS=1 (profiles/README.md)")
+        pytest.skip("storage variants 1-6 are measured dead ends, built only with -DPRX_FULL_VARIANTS=1 (profiles/README.md)")
     assert name.startswith(want)
     s = golden_state(g)
     s.mask[::7] = -1
