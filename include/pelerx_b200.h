@@ -174,6 +174,13 @@ PRX_API int prx_react_state_box(
   prx_handle* h, const int lo[3], const int hi[3], const prx_array4* sold, const prx_array4* snew, const prx_array4* nonrs,
   const prx_array4* I_R, const prx_array4* work, const prx_state_index* ix, double dt, int do_update, void* cuda_stream);
 
+/* Rotating frame of reference (pelec.do_rf, rf_omega, rf_axis, rf_axis_x/y/z; PC/Source/React.cpp:123-131,192-218,245-300):
+ * the kinetic-energy bookkeeping of the react_state body then carries rotenrg = 0.5 omega^2 r^2 (PC/Source/Utilities.H:23-65)
+ * with r the in-plane distance of the cell centre prob_lo + (index + 0.5) dx from the axis through axis_loc.  Box indices
+ * passed to prx_react_state_box(es) are then the level's global cell indices (as AMReX boxes are).  on = 0 switches it off. */
+PRX_API int prx_set_rotating_frame(
+  prx_handle* h, int on, double omega, int axis, const double axis_loc[3], const double prob_lo[3], const double dx[3]);
+
 PRX_API int prx_react_state_boxes(
   prx_handle* h, int nboxes, const int* lo, const int* hi, const prx_array4* sold, const prx_array4* snew,
   const prx_array4* nonrs, const prx_array4* I_R, const prx_array4* work, const prx_state_index* ix, double dt,

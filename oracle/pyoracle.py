@@ -357,14 +357,24 @@ def reacteval_states(lib, ncells_xyz, fuel=None):
 
 # ----------------------------------------------------------------------------------------------
 # PeleC::react_state body (test infrastructure; restated from PC/Source/React.cpp:181-343, numpy)
-# PARITY UNPINNED for the pack / unpack arithmetic: PeleC itself needs its cmake build system (not run here); the reactor
-# call in the middle is the pinned oracle.  Rotating-frame terms omitted (rotenrg = 0), as in the product.
+# PINNED against PeleC::react_state of the unmodified application (oracle/ref_pelec, tests/golden/make_golden3.py,
+# tests/test_react_state_golden.py): bit for bit with ReactorRK64, incl. the rotating-frame terms (pelec.do_rf).
 # ----------------------------------------------------------------------------------------------
 UIDX = dict(urho=0, umx=1, umy=2, umz=3, ueden=4, ueint=5, utemp=6, ufs=7)
 
 
-def react_state_oracle(orc, sold, snew, nonrs, dt, do_update=True, reactor="cvode", **kw):
-    """sold, snew, nonrs: [NVAR, ncells] arrays (NVAR = 7 + N).  Returns (snew_out, I_R [N+2, ncells], FC)."""
+def rot_energy(idx, omega, axis, axis_loc, prob_lo, dx):
+    """get_rot_energy (PC/Source/Utilities.H:23-65): idx [3, ncells] global cell indices -> 0.5 omega^2 r^2 per cell"""
+    r = [(prob_lo[d] + (idx[d] + 0.5) * dx[d]) - axis_loc[d] for d in range(3)]
+    rad2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2]
+    rad2 = rad2 - r[axis] * r[axis]
+    rad = np.sqrt(rad2)
+    return 0.5 * omega * omega * rad * rad
+
+
+def react_state_oracle(orc, sold, snew, nonrs, dt, do_update=True, reactor="cvode", rotenrg=0.0, **kw):
+    """sold, snew, nonrs: [NVAR, ncells] arrays (NVAR = 7 + N).  Returns (snew_out, I_R [N+2, ncells], FC).
+    rotenrg: rotating-frame energy per cell (rot_energy), 0 without pelec.do_rf."""
     u = UIDX
     N = orc.N
     sold, snew, nonrs = (np.array(x, dtype=np.float64) for x in (sold, snew, nonrs))
@@ -373,9 +383,11 @@ def react_state_oracle(orc, sold, snew, nonrs, dt, do_update=True, reactor="cvod
     rhou, rhov, rhow, rho_old = sold[u["umx"]], sold[u["umy"]], sold[u["umz"]], sold[u["urho"]]
     rhoInv = 1.0 / rho_old
     e_old = (sold[u["ueden"]] - 0.5 * (rhou * rhou + rhov * rhov + rhow * rhow) * rhoInv) * rhoInv
+    e_old = e_old + rotenrg
     rhou, rhov, rhow = snew[u["umx"]], snew[u["umy"]], snew[u["umz"]]
     rhoInv = 1.0 / snew[u["urho"]]
-    rhoedot_ext = (snew[u["ueden"]] - 0.5 * (rhou * rhou + rhov * rhov + rhow * rhow) * rhoInv - rho_old * e_old) / dt
+    rhoedot_ext = (snew[u["ueden"]] - 0.5 * (rhou * rhou + rhov * rhov + rhow * rhow) * rhoInv + snew[u["urho"]] * rotenrg
+                   - rho_old * e_old) / dt
     st = BoxState(sold[u["ufs"]:u["ufs"] + N].copy(), sold[u["utemp"]].copy(), sold[u["ueint"]].copy(),
                   nonrs[u["ufs"]:u["ufs"] + N].copy(), rhoedot_ext.copy())
     # ---- React.cpp:222-228 (reactor, current_time = 0)
@@ -392,7 +404,7 @@ def react_state_oracle(orc, sold, snew, nonrs, dt, do_update=True, reactor="cvod
         rhonew = rhonew + st.rY[n]
     out = snew.copy()
     eint_new = rho_old * e_old + dt * rhoedot_ext
-    eden_new = eint_new + 0.5 * (umnew * umnew + vmnew * vmnew + wmnew * wmnew) / rhonew
+    eden_new = eint_new + 0.5 * (umnew * umnew + vmnew * vmnew + wmnew * wmnew) / rhonew - rhonew * rotenrg
     if do_update:
         out[u["urho"]], out[u["umx"]], out[u["umy"]], out[u["umz"]] = rhonew, umnew, vmnew, wmnew
         out[u["ufs"]:u["ufs"] + N] = st.rY

@@ -36,6 +36,8 @@ struct prx_handle
   cudaStream_t stage_stream;
   cudaStream_t in_stream, out_stream; // host staging pipeline of prx_react_box_host: H2D | react | D2H per slab
   bool keep_last_steps;              // react_args: do not reset the per-call step sum (slabs of one call)
+  int rf_on = 0, rf_axis = 2;        // rotating frame of prx_react_state_box(es) (prx_set_rotating_frame)
+  double rf_omega = 0.0, rf_axloc[3] = {0, 0, 0}, rf_problo[3] = {0, 0, 0}, rf_dx[3] = {1, 1, 1};
   char err[512];
 };
 
@@ -612,6 +614,17 @@ static int react_state_one(
   a.ix.utemp = ix->utemp;
   a.ix.ufs = ix->ufs;
   a.do_update = do_update;
+  a.rf_on = h->rf_on;
+  if (h->rf_on) {
+    a.rf_axis = h->rf_axis;
+    a.rf_omega = h->rf_omega;
+    for (int d = 0; d < 3; d++) {
+      a.lo[d] = lo[d];
+      a.rf_axloc[d] = h->rf_axloc[d];
+      a.rf_problo[d] = h->rf_problo[d];
+      a.rf_dx[d] = h->rf_dx[d];
+    }
+  }
   a.dt = dt;
   a.time = 0.0; // React.cpp:171: current_time = 0
   const bool fused = (h->cfg.reactor_kind == PRX_REACTOR_RK64) || h->ops->bdf_is_fused(h->sched);
@@ -658,6 +671,25 @@ static int react_state_one(
     return rc;
   }
   return e == cudaSuccess ? PRX_OK : fail(h, PRX_ERR_CUDA, "react_state pack/unpack", e);
+}
+
+int prx_set_rotating_frame(
+  prx_handle* h, int on, double omega, int axis, const double axis_loc[3], const double prob_lo[3], const double dx[3])
+{
+  if (h == nullptr || (on && (axis < 0 || axis > 2 || !axis_loc || !prob_lo || !dx))) {
+    return PRX_ERR_BAD_ARG;
+  }
+  h->rf_on = on ? 1 : 0;
+  if (on) {
+    h->rf_omega = omega;
+    h->rf_axis = axis;
+    for (int d = 0; d < 3; d++) {
+      h->rf_axloc[d] = axis_loc[d];
+      h->rf_problo[d] = prob_lo[d];
+      h->rf_dx[d] = dx[d];
+    }
+  }
+  return PRX_OK;
 }
 
 int prx_react_state_box(

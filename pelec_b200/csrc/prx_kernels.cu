@@ -140,26 +140,51 @@ __device__ __forceinline__ long long cell_offset(const int c, const int* len, co
 // ---- fused PeleC::react_state body (PC/Source/React.cpp:181-343), one cell ---------------------------------
 // Pack (React.cpp:181-220): the reactor integrates from the OLD state (rhoY, T, rho*e_int of S_old) with the non-reacting
 // species sources and the energy source rhoedot_ext = (rho*e_int implied by S_new = S_old + dt*sources  -  rho_old*e_old) / dt.
-// Rotating-frame energy (pelec.do_rf) is not supported: rotenrg = 0 (adding it is exact-zero arithmetic in the reference).
-__device__ __forceinline__ double state_e_old(const BoxArgs& a, const long long oo, double& rho_old)
+// Rotating frame (pelec.do_rf): rotenrg = get_rot_energy (PC/Source/Utilities.H:23-65) of the cell centre; 0 when off, and then
+// every term below that carries it is exact-zero arithmetic, as in the reference.
+__device__ __forceinline__ double state_rotenrg(const BoxArgs& a, const int c)
+{
+  if (!a.rf_on) {
+    return 0.0;
+  }
+  const int i = c % a.len[0];
+  const int r = c / a.len[0];
+  const int idx[3] = {a.lo[0] + i, a.lo[1] + r % a.len[1], a.lo[2] + r / a.len[1]};
+  double rv[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    rv[d] = (a.rf_problo[d] + (idx[d] + 0.5) * a.rf_dx[d]) - a.rf_axloc[d]; // pc_cmp_loc - axis location
+  }
+  double rad2 = rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2]; // RealVect::radSquared
+  rad2 -= rv[a.rf_axis] * rv[a.rf_axis];                         // only in plane
+  const double rad = sqrt(rad2);
+  return 0.5 * a.rf_omega * a.rf_omega * rad * rad;
+}
+
+__device__ __forceinline__ double state_e_old(const BoxArgs& a, const long long oo, double& rho_old, const double rotenrg)
 {
   const double* so = a.sold.p + oo;
   const long long ns = a.sold.ns;
   const double rhou = so[a.ix.umx * ns], rhov = so[a.ix.umy * ns], rhow = so[a.ix.umz * ns];
   rho_old = so[a.ix.urho * ns];
   const double rhoInv = 1.0 / rho_old;
-  return (so[a.ix.ueden * ns] - 0.5 * (rhou * rhou + rhov * rhov + rhow * rhow) * rhoInv) * rhoInv;
+  double e_old = (so[a.ix.ueden * ns] - 0.5 * (rhou * rhou + rhov * rhov + rhow * rhow) * rhoInv) * rhoInv;
+  e_old += rotenrg;
+  return e_old;
 }
 
 __device__ __forceinline__ double state_rhoedot_ext(const BoxArgs& a, const int c)
 {
   double rho_old;
-  const double e_old = state_e_old(a, cell_offset(c, a.len, a.sold.js, a.sold.ks), rho_old);
+  const double rotenrg = state_rotenrg(a, c);
+  const double e_old = state_e_old(a, cell_offset(c, a.len, a.sold.js, a.sold.ks), rho_old, rotenrg);
   const double* sn = a.snew.p + cell_offset(c, a.len, a.snew.js, a.snew.ks);
   const long long ns = a.snew.ns;
   const double rhou = sn[a.ix.umx * ns], rhov = sn[a.ix.umy * ns], rhow = sn[a.ix.umz * ns];
   const double rhoInv = 1.0 / sn[a.ix.urho * ns];
-  return (sn[a.ix.ueden * ns] - 0.5 * (rhou * rhou + rhov * rhov + rhow * rhow) * rhoInv - rho_old * e_old) / a.dt;
+  return (sn[a.ix.ueden * ns] - 0.5 * (rhou * rhou + rhov * rhov + rhow * rhow) * rhoInv + sn[a.ix.urho * ns] * rotenrg -
+          rho_old * e_old) /
+         a.dt;
 }
 
 // Unpack + I_R + heat release (React.cpp:233-343) from the reactor's output (rhoY_new[N], T_new) of one cell.
@@ -177,7 +202,8 @@ __device__ __forceinline__ void state_unpack(
   const long long sos = a.sold.ns, nrs = a.nonrs.ns, sns = a.snew.ns, irs = a.IR.ns;
   const double dt = a.dt;
   double rho_old;
-  const double e_old = state_e_old(a, oo, rho_old);
+  const double rotenrg = state_rotenrg(a, c);
+  const double e_old = state_e_old(a, oo, rho_old, rotenrg);
   const double umnew = so[a.ix.umx * sos] + dt * nr[a.ix.umx * nrs];
   const double vmnew = so[a.ix.umy * sos] + dt * nr[a.ix.umy * nrs];
   const double wmnew = so[a.ix.umz * sos] + dt * nr[a.ix.umz * nrs];
@@ -187,7 +213,7 @@ __device__ __forceinline__ void state_unpack(
     rhonew += rhoY[n];
   }
   const double eint_new = rho_old * e_old + dt * rhoedot_ext;
-  const double eden_new = eint_new + 0.5 * (umnew * umnew + vmnew * vmnew + wmnew * wmnew) / rhonew;
+  const double eden_new = eint_new + 0.5 * (umnew * umnew + vmnew * vmnew + wmnew * wmnew) / rhonew - rhonew * rotenrg;
   double T_h = Tnew;
   if (a.do_update) {
     sn[a.ix.urho * sns] = rhonew;

@@ -50,6 +50,10 @@ struct BoxArgs
   ArrView sold, snew, nonrs, IR;
   StateIx ix;
   int do_update; // !react_init
+  // rotating frame (pelec.do_rf, React.cpp:123-131): rotenrg = 0.5 omega^2 r^2 with r the distance of the cell centre from
+  // the axis; lo = global index of the box's first cell
+  int rf_on, rf_axis, lo[3];
+  double rf_omega, rf_axloc[3], rf_problo[3], rf_dx[3];
   double dt, time;
   const int* order; // optional: queue position -> cell index (cells sorted by temperature), nullptr = identity
 };

@@ -284,6 +284,12 @@ class ReactorB200:
         ix.nvar = ufs + nspec if nvar is None else nvar
         return ix
 
+    def set_rotating_frame(self, omega, axis, axis_loc, prob_lo, dx, on=True):
+        """pelec.do_rf / rf_omega / rf_axis / rf_axis_{x,y,z} + the level's geometry (PC/Source/React.cpp:123-131)"""
+        d3 = C.c_double * 3
+        self.lib.prx_set_rotating_frame.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, d3, d3, d3]
+        self._check(self.lib.prx_set_rotating_frame(self.h, int(bool(on)), float(omega), int(axis), d3(*axis_loc), d3(*prob_lo), d3(*dx)))
+
     def react_state(self, box, sold, snew, nonrs, I_R, dt, do_update=True, work=None, ix=None, stream=None):
         lo = (C.c_int * 3)(*box.lo)
         hi = (C.c_int * 3)(*box.hi)

@@ -24,7 +24,11 @@ DT = 1e-7
 NSUB = 640  # cells kept in the fixture
 
 
+RF = {"omega": 4.0e4, "axis": 2, "axis_loc": (0.11, 0.07, 0.0)}  # rotating-frame variant (pelec.do_rf)
+
+
 def worker(mech, integ, out):
+    rf = out.endswith("_rf.npz")
     lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libpelec_pmf_%s.so" % mech))
     args = ["pelec", CASE + "/pmf-lidryer-cvode.inp", "amr.plot_files_output=0", "amr.checkpoint_files_output=0",
             "pelec.xNormPlane.int=100000", "prob.pmf_datafile=" + CASE + "/LiDryer_H2_p1_phi0_4000tu0300.dat",
@@ -32,6 +36,9 @@ def worker(mech, integ, out):
             "pelec.chem_integrator=" + integ, "cvode.solve_type=denseAJ_direct", "ode.analytical_jacobian=1",
             "ode.rtol=%r" % PARAMS["rtol"], "ode.atol=%r" % PARAMS["atol"], "cvode.max_order=%d" % PARAMS["max_order"],
             "ode.clean_init_massfrac=0"]
+    if rf:
+        args += ["pelec.do_rf=1", "pelec.do_mol=1", "pelec.rf_omega=%r" % RF["omega"], "pelec.rf_axis=%d" % RF["axis"],
+                 "pelec.rf_axis_x=%r" % RF["axis_loc"][0], "pelec.rf_axis_y=%r" % RF["axis_loc"][1], "pelec.rf_axis_z=%r" % RF["axis_loc"][2]]
     argv = (C.c_char_p * len(args))(*[a.encode() for a in args])
     lib.pelecref_init.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
     lib.pelecref_ncells.restype = C.c_long
@@ -67,6 +74,26 @@ def worker(mech, integ, out):
         lib.pelecref_set(0, 1, snew_app.ctypes.data)
         lib.pelecref_react_state(0, DT, react_init, None if react_init else aux.ctypes.data)
         res[tag] = (get(1, nvar), get(2, N + 2))
+    if rf:
+        # every cell of the box with the strongest heat release, with its global indices: rotenrg depends on the position
+        lib.pelecref_boxes.argtypes = [C.c_int, C.c_void_p]
+        nb = lib.pelecref_nboxes(0)
+        bx = np.zeros(6 * nb, dtype=np.int32)
+        lib.pelecref_boxes(0, bx.ctypes.data)
+        bx = bx.reshape(nb, 6)
+        sizes = [int(np.prod(b[3:] - b[:3] + 1)) for b in bx]
+        starts = np.concatenate([[0], np.cumsum(sizes)])
+        hr = np.abs(res["update"][1][N + 1])
+        b = int(np.argmax([hr[starts[i]:starts[i + 1]].max() for i in range(nb)]))
+        sel = np.arange(starts[b], starts[b + 1])
+        np.savez_compressed(
+            out, mech=mech, integrator=integ, dt=DT, atol=PARAMS["atol"], sold=sold[:, sel], aux=aux[:, sel],
+            snew_out=res["update"][0][:, sel], I_R=res["update"][1][:, sel], box_lo=bx[b, :3], box_hi=bx[b, 3:],
+            omega=RF["omega"], axis=RF["axis"], axis_loc=np.array(RF["axis_loc"]), prob_lo=np.array([0.0, 0.0, 1.0]),
+            dx=np.array([0.3125 / 8, 0.3125 / 8, 5.0 / 128]),
+            note="PeleC::react_state with pelec.do_rf = 1 (rotating frame), one whole box - tests/golden/make_golden3.py")
+        print("%s %s rotating frame: box %d, %d cells, max |heat release| %.3e" % (mech, integ, b, sel.size, hr[sel].max()))
+        return
     # subset: whole z-columns (the profile varies along z, cells of a column are 64 apart in the flat order of a box)
     flame = np.argsort(-np.abs(res["update"][1][N + 1]))[: NSUB // 2]  # strongest heat release
     rest = rng.choice(nc, NSUB - flame.size, replace=False)
@@ -87,7 +114,7 @@ def main():
         worker(sys.argv[1], sys.argv[2], sys.argv[3])
         return
     here = os.path.dirname(os.path.abspath(__file__))
-    for integ, tag in (("ReactorCvode", "cvode"), ("ReactorRK64", "rk64")):
+    for integ, tag in (("ReactorCvode", "cvode"), ("ReactorRK64", "rk64"), ("ReactorRK64", "rk64_rf")):
         out = os.path.join(here, "react_state_pmf_LiDryer_%s.npz" % tag)
         tmp = "/tmp/pelec_golden_%s" % tag
         os.makedirs(tmp, exist_ok=True)

@@ -74,6 +74,63 @@ def test_restated_react_state_matches_pelec(tag):
     del gi
 
 
+def rf_case():
+    from oracle.pyoracle import rot_energy
+    g = load("rk64_rf")
+    lo, hi = g["box_lo"], g["box_hi"]
+    shape = tuple(int(hi[d] - lo[d] + 1) for d in range(3))
+    c = np.arange(shape[0] * shape[1] * shape[2])
+    idx = np.stack([lo[0] + c % shape[0], lo[1] + (c // shape[0]) % shape[1], lo[2] + c // (shape[0] * shape[1])])
+    rot = rot_energy(idx, float(g["omega"]), int(g["axis"]), g["axis_loc"], g["prob_lo"], g["dx"])
+    return g, shape, rot
+
+
+def test_restated_react_state_with_rotating_frame_matches_pelec():
+    """pelec.do_rf = 1 (React.cpp:123-131, 192-218, 245-300): one whole box of the PMF level with its global indices"""
+    g, shape, rot = rf_case()
+    assert rot.min() > 0 and rot.max() > 10 * rot.min()  # the term is exercised, and varies over the box
+    orc = Oracle("LiDryer")
+    dt = float(g["dt"])
+    sold, aux = g["sold"], g["aux"]
+    got_snew, got_IR, _ = react_state_oracle(orc, sold, sold + dt * aux, aux, dt, True, "rk64", rotenrg=rot, atol=float(g["atol"]))
+    assert np.array_equal(got_snew, g["snew_out"]) and np.array_equal(got_IR, g["I_R"])  # bit for bit
+
+
+@pytest.mark.gpu
+def test_gpu_react_state_with_rotating_frame_matches_pelec():
+    torch = pytest.importorskip("torch")
+    from pelec_b200.reactor import Array4, Box, ReactorB200
+    g, shape, rot = rf_case()
+    dev = torch.device("cuda:0")
+    N, dt = 9, float(g["dt"])
+    nx, ny, nz = shape
+    lo, hi = [int(v) for v in g["box_lo"]], [int(v) for v in g["box_hi"]]
+    r = ReactorB200.create("ReactorRK64", "LiDryer", ode__atol=float(g["atol"]))
+    r.init(1, 1)
+    r.set_rotating_frame(float(g["omega"]), int(g["axis"]), g["axis_loc"], g["prob_lo"], g["dx"])
+
+    def fab(a):
+        return torch.from_numpy(np.ascontiguousarray(a).reshape(a.shape[0], nz, ny, nx).copy()).to(dev)
+    sold, aux = g["sold"], g["aux"]
+    t_old, t_new, t_src = fab(sold), fab(sold + dt * aux), fab(aux)
+    t_IR = torch.zeros((N + 2, nz, ny, nx), dtype=torch.float64, device=dev)
+    A = lambda t: Array4(t, lo)  # the FAB starts at the box's global lo
+    r.react_state(Box(lo, hi), A(t_old), A(t_new), A(t_src), A(t_IR), dt)
+    torch.cuda.synchronize()
+    got_snew = t_new.reshape(t_new.shape[0], -1).cpu().numpy()
+    got_IR = t_IR.reshape(N + 2, -1).cpu().numpy()
+    species_bar = 1e-10 * np.maximum(np.abs(g["snew_out"][7:]), 1e-2 * g["snew_out"][0][None, :])
+    compare(g, N, got_snew, got_IR, g["snew_out"], g["I_R"], dt, species_bar, 1e-11)
+    # and the term really is in there: without the frame rho*e_int differs (rho*E does not: the term cancels in it when mass
+    # is conserved, UEDEN_new = UEDEN_in - KE_in + KE_new + (rho_in - rho_new) rotenrg)
+    r.set_rotating_frame(0.0, 2, (0, 0, 0), (0, 0, 0), (1, 1, 1), on=False)
+    t_new2 = fab(sold + dt * aux)
+    r.react_state(Box(lo, hi), A(t_old), A(t_new2), A(t_src), A(t_IR), dt)
+    torch.cuda.synchronize()
+    assert (t_new2[5] - t_new[5]).abs().max().item() > 1e-4 * t_new[5].abs().max().item()
+    r.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("tag", ["rk64", "cvode"])
 def test_gpu_react_state_matches_pelec(tag):
