@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PRX_ABI_VERSION 1
+#define PRX_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define PRX_API __attribute__((visibility("default")))
@@ -52,8 +52,12 @@ typedef enum {
 /* pelec.chem_integrator / chem_integrator keys (PC/Source/Params/_cpp_parameters:302-305) */
 typedef enum {
   PRX_REACTOR_RK64 = 0,      /* "ReactorRK64"  PP/Source/Reactions/ReactorRK64.cpp:166-320  */
-  PRX_REACTOR_CVODE = 1      /* "ReactorCvode" PP/Source/Reactions/ReactorCvode.cpp:1267-1489,
+  PRX_REACTOR_CVODE = 1,     /* "ReactorCvode" PP/Source/Reactions/ReactorCvode.cpp:1267-1489,
                                 per-cell (CPU-branch) semantics: one BDF integration per cell */
+  PRX_REACTOR_ARKODE = 2     /* "ReactorArkode" PP/Source/Reactions/ReactorArkode.cpp:135-260 (ode.use_erkstep = 1, the default):
+                                ARKODE's adaptive explicit Runge-Kutta stepper on the WHOLE BOX as one system - one step
+                                size and one WRMS error norm for all cells of a react call, as the reference does on every
+                                backend; FC = the box's RHS-evaluation count in every cell.  Array4 react only. */
 } prx_reactor_kind;
 
 /* cvode.solve_type (PP/Source/Reactions/ReactorCvode.cpp:507-934) */
@@ -80,6 +84,9 @@ typedef struct prx_config {
   int clean_init_massfrac;  /* ode.clean_init_massfrac (0) */
   int verbose;              /* ode.verbose */
   int device;               /* CUDA device ordinal, -1 = current device */
+  int ark_method;           /* ode.rk_method (ReactorArkode.cpp:26-88): 40 Zonneveld 5-3-4 (default), 20 Heun-Euler 2-1-2,
+                               30 Bogacki-Shampine 4-2-3 */
+  int ark_controller;       /* ode.rk_controller (ReactorArkode.cpp:90-116): 0 PID (default), 1 PI, 2 I */
 } prx_config;
 
 /* Same fields and meaning as amrex::Array4<T> (AMR/Src/Base/AMReX_Array4.H:60-68):

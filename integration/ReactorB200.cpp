@@ -89,7 +89,7 @@ int ReactorB200<KIND>::init(int reactor_type, int /*ncells*/)
 
   prx_config cfg;
   prx_default_config(&cfg);
-  cfg.reactor_kind = (KIND == b200::CVODE) ? PRX_REACTOR_CVODE : PRX_REACTOR_RK64;
+  cfg.reactor_kind = (KIND == b200::CVODE) ? PRX_REACTOR_CVODE : ((KIND == b200::ARKODE) ? PRX_REACTOR_ARKODE : PRX_REACTOR_RK64);
   cfg.reactor_type = reactor_type;
 
   // the mechanism is the one this executable was compiled for (Chemistry_Model)
@@ -114,6 +114,16 @@ int ReactorB200<KIND>::init(int reactor_type, int /*ncells*/)
   pp.query("clean_init_massfrac", clean);
   cfg.clean_init_massfrac = clean ? 1 : 0;
   cfg.verbose = this->verbose;
+  if (KIND == b200::ARKODE) {
+    // ReactorArkode.cpp:13-21: ode.use_erkstep (1), ode.rk_method (40), ode.rk_controller (0)
+    int use_erkstep = 1;
+    pp.query("use_erkstep", use_erkstep);
+    if (use_erkstep != 1) {
+      amrex::Abort("ReactorArkodeB200: ode.use_erkstep = 0 (ARKStep with an explicit table) is not implemented; use the ERKStep default");
+    }
+    pp.query("rk_method", cfg.ark_method);
+    pp.query("rk_controller", cfg.ark_controller);
+  }
   if (KIND == b200::CVODE) {
     amrex::ParmParse ppcv("cvode");
     ppcv.query("max_order", cfg.max_order);
@@ -370,5 +380,6 @@ void ReactorB200<KIND>::unflatten(
 
 template class ReactorB200<b200::CVODE>;
 template class ReactorB200<b200::RK64>;
+template class ReactorB200<b200::ARKODE>;
 
 } // namespace pele::physics::reactions

@@ -315,6 +315,30 @@ class Reference:
         self._parm("ode", "verbose", 0)
         return self._react("ReactorRK64", st, dt, time, reactor_type)
 
+    def react_arkode(self, states, dt, time=0.0, rtol=1e-6, atol=1e-10, rk_method=40, rk_controller=0, typ_vals=None, reactor_type=1):
+        """ReactorArkode (ERKStep) on a SEQUENCE of boxes with ONE reactor object, as PeleC's MFIter loop does: each state is
+        one box (ncells x 1 x 1) integrated as one coupled system; the reactor's step-size controller is created once in init()
+        and keeps its history from call to call (ReactorArkode.cpp:90-116, 207).  Returns react()'s ints (nfe per call)."""
+        self._parm("ode", "rtol", repr(rtol))
+        self._parm("ode", "atol", repr(atol))
+        self._parm("ode", "verbose", 0)
+        self._parm("ode", "use_erkstep", 1)
+        self._parm("ode", "rk_method", rk_method)
+        self._parm("ode", "rk_controller", rk_controller)
+        self._parm("ode", "clean_init_massfrac", 0)
+        h = self.lib.peleref_reactor_create(b"ReactorArkode", reactor_type, 1)
+        out = []
+        try:
+            if typ_vals is not None:
+                tv = np.ascontiguousarray(typ_vals, dtype=float)
+                self.lib.peleref_reactor_set_typ_vals(h, _p(tv), len(tv))
+            for st in states:
+                out.append(self.lib.peleref_react_box(h, st.ncells, 1, 1, _p(st.rY), _p(st.rYsrc), _p(st.T), _p(st.rE),
+                                                      _p(st.rEsrc), _p(st.FC), st.mask.ctypes.data_as(ip), dt, time))
+        finally:
+            self.lib.peleref_reactor_destroy(h)
+        return out
+
     def react_cvode(self, st, dt, time=0.0, rtol=1e-10, atol=1e-10, max_order=2, solve_type="denseAJ_direct",
                     typ_vals=None, reactor_type=1, max_nls_iters=3, clean_init_massfrac=False, want_stats=False):
         self._parm("ode", "rtol", repr(rtol))

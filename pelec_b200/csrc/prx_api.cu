@@ -4,12 +4,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <atomic>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <new>
 #include <vector>
 
 #include "prx_kernels.cuh"
+#include "prx_arkode.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <nvtx3/nvToolsExt.h> // header-only (dlopens the injection library of an attached profiler; no link dependency)
@@ -36,6 +38,9 @@ struct prx_handle
   cudaStream_t stage_stream;
   cudaStream_t in_stream, out_stream; // host staging pipeline of prx_react_box_host: H2D | react | D2H per slab
   bool keep_last_steps;              // react_args: do not reset the per-call step sum (slabs of one call)
+  ark::Controller ark_ctl;           // ReactorArkode: the step-size controller's history persists across react calls
+  ark::Table ark_tab;                //                the Butcher table of cfg.ark_method
+  long long ark_last_nfe = 0, ark_nfe = 0, ark_nst = 0, ark_netf = 0, ark_too_much_work = 0, ark_cells = 0;
   int rf_on = 0, rf_axis = 2;        // rotating frame of prx_react_state_box(es) (prx_set_rotating_frame)
   double rf_omega = 0.0, rf_axloc[3] = {0, 0, 0}, rf_problo[3] = {0, 0, 0}, rf_dx[3] = {1, 1, 1};
   char err[512];
@@ -240,6 +245,8 @@ int prx_default_config(prx_config* cfg)
   cfg->clean_init_massfrac = 0;
   cfg->verbose = 0;
   cfg->device = -1;
+  cfg->ark_method = 40;    // ReactorArkode.H: rk_method{40} = ARKODE_ZONNEVELD_5_3_4
+  cfg->ark_controller = 0; // PID
   return PRX_OK;
 }
 
@@ -272,8 +279,17 @@ int prx_create(const prx_config* cfg, prx_handle** out)
   if (ops == nullptr) {
     return PRX_ERR_BAD_ARG;
   }
-  if (cfg->reactor_kind != PRX_REACTOR_RK64 && cfg->reactor_kind != PRX_REACTOR_CVODE) {
+  if (cfg->reactor_kind != PRX_REACTOR_RK64 && cfg->reactor_kind != PRX_REACTOR_CVODE && cfg->reactor_kind != PRX_REACTOR_ARKODE) {
     return PRX_ERR_BAD_ARG;
+  }
+  ark::Table ark_tab;
+  if (cfg->reactor_kind == PRX_REACTOR_ARKODE) {
+    if (!(cfg->rtol > 0.0) || !(cfg->atol > 0.0)) {
+      return PRX_ERR_BAD_ARG;
+    }
+    if (!ark::table_for(cfg->ark_method, &ark_tab) || cfg->ark_controller < 0 || cfg->ark_controller > 2) {
+      return PRX_ERR_UNSUPPORTED; // the other ERK tables / the explicit-Gustafsson controller of ReactorArkode.cpp:26-116
+    }
   }
   if (cfg->reactor_type != 1 && cfg->reactor_type != 2) {
     return PRX_ERR_BAD_ARG; // reference: amrex::Abort("Wrong reactor type. Choose between 1 (e) or 2 (h).")
@@ -285,7 +301,7 @@ int prx_create(const prx_config* cfg, prx_handle** out)
     if (cfg->solve_type != PRX_SOLVE_DENSE_AJ_DIRECT && cfg->solve_type != PRX_SOLVE_DENSE_DIRECT) {
       return PRX_ERR_UNSUPPORTED;
     }
-  } else {
+  } else if (cfg->reactor_kind == PRX_REACTOR_RK64) {
     if (cfg->rk64_nsubsteps_guess < 1 || cfg->rk64_nsubsteps_min < 1 || cfg->rk64_nsubsteps_max < 1 || !(cfg->atol > 0.0)) {
       return PRX_ERR_BAD_ARG;
     }
@@ -311,6 +327,8 @@ int prx_create(const prx_config* cfg, prx_handle** out)
   h->cfg = *cfg;
   h->ops = ops;
   h->device = dev;
+  h->ark_tab = ark_tab;
+  h->ark_ctl.init(cfg->ark_controller); // ReactorArkode::init creates the SUNAdaptController once (ReactorArkode.cpp:90-116)
   h->typ_vals.assign(ops->num_species + 1, -1.0);
   h->d_stats = nullptr;
   h->n_box_streams = 0;
@@ -526,6 +544,329 @@ static int react_args(prx_handle* h, const BoxArgs& a, cudaStream_t stream)
   return PRX_OK;
 }
 
+// ---- ReactorArkode::react, Array4 (PP/Source/Reactions/ReactorArkode.cpp:135-260): see prx_arkode.cuh ---------------------
+static int react_arkode(prx_handle* h, const BoxArgs& a, cudaStream_t stream)
+{
+  NvtxRange nvtx("prx::ReactorArkode::react");
+  DeviceGuard g(h->device);
+  const MechOps* ops = h->ops;
+  const ark::Table& B = h->ark_tab;
+  const int N = ops->num_species, neq = N + 1;
+  const long long nc = a.ncells, n = nc * neq;
+  const double uround = 2.220446049250313e-16;
+  // device vectors: yn, ycur, yold, fold, ewt, tmp, F[stages] (neq columns each), rYsrc (N), rhoe, rhoesrc, atol (neq), scratch
+  const int nvec = 6 + B.stages;
+  const size_t doubles = (size_t)nvec * n + (size_t)N * nc + 2 * (size_t)nc + (size_t)neq + 2 * ark::RG + 2;
+  double* buf = nullptr;
+  if (cudaMallocAsync((void**)&buf, doubles * sizeof(double) + (size_t)nc * sizeof(long long), stream) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(h, PRX_ERR_ALLOC, "ReactorArkode work vectors");
+  }
+  double* yn = buf;
+  double* ycur = yn + n;
+  double* yold = ycur + n;
+  double* fold = yold + n;
+  double* ewt = fold + n;
+  double* tmp = ewt + n;
+  double* F[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (int sidx = 0; sidx < B.stages; sidx++) {
+    F[sidx] = tmp + (size_t)(sidx + 1) * n;
+  }
+  double* rYsrc = tmp + (size_t)(B.stages + 1) * n;
+  double* rhoe = rYsrc + (size_t)N * nc;
+  double* rhoesrc = rhoe + nc;
+  double* atolv = rhoesrc + nc;
+  double* part = atolv + neq;
+  double* red = part + 2 * ark::RG;
+  long long* fcunt = reinterpret_cast<long long*>(buf + doubles);
+  int rc = PRX_OK;
+  long long nfe = 0;
+  double host_red[2] = {0.0, 0.0};
+  auto fetch = [&]() { // reduce the block partials and bring (sum, max) to the host
+    ark::finish_kernel<<<1, 32, 0, stream>>>(part, red);
+    cudaMemcpyAsync(host_red, red, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream);
+    return cudaStreamSynchronize(stream);
+  };
+  auto wrms = [&](double sumsq) { return std::sqrt(sumsq / (double)n); };
+  auto rhs_at = [&](double t, const double* y, double* f) { // plain f(t, y)
+    ArkStageArgs s;
+    std::memset(&s, 0, sizeof(s));
+    s.ncells = a.ncells;
+    s.reactor_type = h->cfg.reactor_type;
+    s.nterms = 0;
+    s.t = t;
+    s.yn = y;
+    s.ycur = nullptr;
+    s.fout = f;
+    s.rhoe = rhoe;
+    s.rhoesrc = rhoesrc;
+    s.rYsrc = rYsrc;
+    nfe++;
+    return ops->ark_stage(s, stream);
+  };
+#define ARK_CUDA(call)                                         \
+  do {                                                         \
+    const cudaError_t e_ = (call);                             \
+    if (e_ != cudaSuccess && rc == PRX_OK) {                   \
+      rc = fail(h, PRX_ERR_CUDA, #call, e_);                   \
+    }                                                          \
+  } while (0)
+  do {
+    // absolute tolerances as set_sundials_solver_tols builds them (ReactorUtils.H:119-141)
+    std::vector<double> atol_h(neq);
+    for (int k = 0; k < neq; k++) {
+      atol_h[k] = (h->typ_vals[0] > 0.0) ? h->typ_vals[k] * h->cfg.atol : h->cfg.atol;
+    }
+    ARK_CUDA(cudaMemcpyAsync(atolv, atol_h.data(), neq * sizeof(double), cudaMemcpyHostToDevice, stream));
+    // flatten (CYOrder), incl. the initial T solve of box_flatten
+    ARK_CUDA(ops->flatten(a, h->cfg, 1, yn, rYsrc, rhoe, rhoesrc, stream));
+    const double t0 = a.time, tout = a.time + a.dt;
+    double tn = t0, tcur = t0;
+    // ---- arkInitialSetup: error weights, f(t0, y0), initial step
+    ark::ewt_kernel<<<ark::RG, ark::RB, 0, stream>>>(n, nc, yn, h->cfg.rtol, atolv, ewt, part);
+    ARK_CUDA(fetch());
+    if (rc != PRX_OK) {
+      break;
+    }
+    if (host_red[1] != 0.0) {
+      rc = fail(h, PRX_ERR_BAD_ARG, "ReactorArkode: a component of the initial error weight is not positive (ARK_ILL_INPUT)");
+      break;
+    }
+    double yn_sumsq = host_red[0]; // sum (yn ewt)^2 of the current error weights: the "too much accuracy" test of every step
+    const double tdiff = tout - tcur;
+    const double tdist = std::fabs(tdiff), tround = uround * std::fmax(std::fabs(tcur), std::fabs(tout));
+    if (tdiff == 0.0 || tdist < 2.0 * tround) {
+      rc = fail(h, PRX_ERR_BAD_ARG, "ReactorArkode: tout too close to t0 (ARK_TOO_CLOSE)");
+      break;
+    }
+    const double sign = (tdiff > 0.0) ? 1.0 : -1.0;
+    ARK_CUDA(rhs_at(tn, yn, F[0])); // step_fullrhs(ARK_FULLRHS_START): fn = F[0]
+    double hstep;
+    {
+      // arkHin
+      const double hlb = 100.0 * tround;
+      ark::hub_kernel<<<ark::RG, ark::RB, 0, stream>>>(n, yn, F[0], ewt, part);
+      ARK_CUDA(fetch());
+      double hub = 0.1 * tdist;
+      if (hub * host_red[1] > 1.0) {
+        hub = 1.0 / host_red[1];
+      }
+      double hg = std::sqrt(hlb * hub);
+      if (hub < hlb) {
+        hstep = sign * hg;
+      } else {
+        double hnew = hg;
+        for (int count1 = 1; count1 <= 4; count1++) {
+          const double hgs = hg * sign;
+          ark::axpy_kernel<<<ark::RG, ark::RB, 0, stream>>>(n, hgs, F[0], yn, ycur);
+          ARK_CUDA(rhs_at(tcur + hgs, ycur, tmp));
+          ark::ydd_kernel<<<ark::RG, ark::RB, 0, stream>>>(n, 1.0 / hgs, tmp, F[0], ewt, part);
+          ARK_CUDA(fetch());
+          const double yddnrm = wrms(host_red[0]);
+          hnew = (yddnrm * hub * hub > 2.0) ? std::sqrt(2.0 / yddnrm) : std::sqrt(hg * hub);
+          if (count1 == 4) {
+            break;
+          }
+          const double hrat = hnew / hg;
+          if (hrat > 0.5 && hrat < 2.0) {
+            break;
+          }
+          if (count1 > 1 && hrat > 2.0) {
+            hnew = hg;
+            break;
+          }
+          hg = hnew;
+        }
+        double h0 = 0.5 * hnew;
+        h0 = h0 < hlb ? hlb : h0;
+        h0 = h0 > hub ? hub : h0;
+        hstep = sign * h0;
+      }
+    }
+    if (rc != PRX_OK) {
+      break;
+    }
+    double etamax = 10000.0; // etamx1: first step
+    double eta = 1.0, hprime = hstep;
+    bool initsetup = true, fn_is_current = true;
+    bool stiffly_accurate = true; // ARKodeButcherTable_IsStifflyAccurate: b == last row of A
+    for (int j = 0; j < B.stages; j++) {
+      stiffly_accurate = stiffly_accurate && (std::fabs(B.b[j] - B.A[B.stages - 1][j]) <= 100.0 * uround);
+    }
+    double told_i = tcur, tnew_i = tcur, h_i = 0.0; // Hermite interpolation data (yold, fold in device vectors)
+    long nstloc = 0;
+    bool done = false;
+    while (!done && rc == PRX_OK) {
+      if (!initsetup) {
+        ark::ewt_kernel<<<ark::RG, ark::RB, 0, stream>>>(n, nc, yn, h->cfg.rtol, atolv, ewt, part);
+        ARK_CUDA(fetch());
+        if (host_red[1] != 0.0) {
+          break; // ARK_ILL_INPUT: the reference returns yn (ReactorArkode ignores the flag)
+        }
+        yn_sumsq = host_red[0];
+      }
+      if (nstloc >= 500) { // MXSTEP_DEFAULT: ARK_TOO_MUCH_WORK, the reference carries on with yn at tcur
+        h->ark_too_much_work++;
+        break;
+      }
+      if (uround * wrms(yn_sumsq) > 1.0) {
+        break; // ARK_TOO_MUCH_ACC
+      }
+      if (hprime != hstep) {
+        hstep = hstep * eta;
+      }
+      int nef = 0;
+      double dsm = 0.0;
+      bool step_ok = false;
+      for (;;) { // attempts
+        if (!fn_is_current) { // erkStep_FullRHS(ARK_FULLRHS_END)
+          if (stiffly_accurate) {
+            ARK_CUDA(cudaMemcpyAsync(F[0], F[B.stages - 1], n * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+          } else {
+            ARK_CUDA(rhs_at(tn, yn, F[0]));
+          }
+          fn_is_current = true;
+        }
+        for (int is = 1; is < B.stages; is++) {
+          ArkStageArgs s;
+          std::memset(&s, 0, sizeof(s));
+          s.ncells = a.ncells;
+          s.reactor_type = h->cfg.reactor_type;
+          s.t = tn + B.c[is] * hstep;
+          for (int js = 0; js < is; js++) {
+            if (B.A[is][js] != 0.0) { // zero terms add an exact zero in the reference's linear combination
+              s.coef[s.nterms] = hstep * B.A[is][js];
+              s.F[s.nterms] = F[js];
+              s.nterms++;
+            }
+          }
+          s.yn = yn;
+          s.ycur = ycur;
+          s.fout = F[is];
+          s.rhoe = rhoe;
+          s.rhoesrc = rhoesrc;
+          s.rYsrc = rYsrc;
+          if (s.nterms == 0) { // cannot happen for a consistent table with c > 0; keep the kernel's contract
+            s.coef[0] = 0.0;
+            s.F[0] = F[0];
+            s.nterms = 1;
+          }
+          nfe++;
+          ARK_CUDA(ops->ark_stage(s, stream));
+        }
+        ark::CombineArgs ca;
+        std::memset(&ca, 0, sizeof(ca));
+        ca.stages = B.stages;
+        for (int j = 0; j < B.stages; j++) {
+          ca.cb[j] = hstep * B.b[j];
+          ca.ce[j] = hstep * (B.b[j] - B.d[j]);
+          ca.F[j] = F[j];
+        }
+        ark::combine_kernel<<<ark::RG, ark::RB, 0, stream>>>(n, ca, yn, ewt, ycur, part);
+        ARK_CUDA(fetch());
+        if (rc != PRX_OK) {
+          break;
+        }
+        dsm = wrms(host_red[0]);
+        // arkCheckTemporalError -> arkAdapt
+        {
+          const int controller_order = B.p + (-1); // pq = 0: embedding order + ADJUST
+          double h_acc = h->ark_ctl.estimate(hstep, controller_order, dsm);
+          const double int_dir = hstep / std::fabs(hstep);
+          double h_cfl = 1.0e30 * std::fabs(hstep); // arkExpStab returns 0: no explicit stability limit
+          h_acc *= 0.99; // ERKStep's own safety factor (erkStep_SetDefaults, arkode_erkstep_io.c:311), not ARKODE's 0.96
+          h_cfl *= 0.5 * int_dir;
+          h_acc = int_dir * std::fmin(std::fabs(h_acc), std::fabs(etamax * hstep));
+          h_acc = int_dir * std::fmax(std::fabs(h_acc), std::fabs(0.1 * hstep));
+          h_acc = int_dir * std::fmin(std::fabs(h_acc), std::fabs(h_cfl));
+          if (dsm <= 1.0) {
+            if ((std::fabs(h_acc) > std::fabs(hstep * 1.0 * 0.999999)) && (std::fabs(h_acc) < std::fabs(hstep * 1.5 * 1.000001))) {
+              h_acc = hstep;
+            }
+          }
+          eta = h_acc / hstep;
+          eta = std::fmax(eta, 0.0 / std::fabs(hstep));        // hmin = 0
+          eta /= std::fmax(1.0, std::fabs(hstep) * 0.0 * eta); // hmax_inv = 0
+        }
+        eta = std::fmin(eta, etamax);
+        eta = std::fmax(eta, 0.0);
+        eta /= std::fmax(1.0, 0.0);
+        if (dsm <= 1.0) {
+          step_ok = true;
+          break;
+        }
+        nef++;
+        h->ark_netf++;
+        if (nef == 7) { // MAXNEF: ARK_ERR_FAILURE
+          break;
+        }
+        etamax = 1.0;
+        if (nef >= 2) {
+          eta = std::fmin(eta, 0.3); // ETAMXF from the SMALL_NEF-th failure on
+        }
+        eta = std::fmin(eta, etamax);
+        hstep *= eta;
+        hprime = hstep;
+      }
+      if (!step_ok || rc != PRX_OK) {
+        break; // the reference's arkHandleFailure: yout = yn
+      }
+      // arkCompleteStep
+      tcur = tn + hstep;
+      ARK_CUDA(cudaMemcpyAsync(yold, yn, n * sizeof(double), cudaMemcpyDeviceToDevice, stream)); // arkInterpUpdate_Hermite
+      ARK_CUDA(cudaMemcpyAsync(fold, F[0], n * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+      told_i = tnew_i;
+      tnew_i = tcur;
+      h_i = hstep;
+      std::swap(yn, ycur); // yn <- ycur
+      fn_is_current = false;
+      h->ark_ctl.update(hstep, dsm);
+      h->ark_nst++;
+      tn = tcur;
+      hprime = hstep * eta;
+      etamax = 25.0; // ERKStep's growth factor (arkode_erkstep_io.c:312), not ARKODE's 20
+      initsetup = false;
+      nstloc++;
+      if ((tcur - tout) * hstep >= 0.0) { // ARK_NORMAL: tout reached, interpolate back (ARKodeGetDky)
+        const double tau = (tout - tcur) / hstep;
+        if (stiffly_accurate) {
+          ARK_CUDA(cudaMemcpyAsync(F[0], F[B.stages - 1], n * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+        } else {
+          ARK_CUDA(rhs_at(tn, yn, F[0])); // fn at the new point
+        }
+        fn_is_current = true;
+        const double tau2 = tau * tau, tau3 = tau * tau2;
+        const int deg = B.q - 1 < 3 ? B.q - 1 : 3; // interp degree min(5, q - 1); the tables here have q <= 4
+        if (deg >= 3) {
+          ark::interp_kernel<<<ark::RG, ark::RB, 0, stream>>>(
+            n, 3.0 * tau2 + 2.0 * tau3, 1.0 - 3.0 * tau2 - 2.0 * tau3, h_i * (tau2 + tau3), h_i * (tau + 2.0 * tau2 + tau3), yold,
+            yn, fold, F[0], ycur);
+        } else if (deg == 2) {
+          ark::interp_kernel<<<ark::RG, ark::RB, 0, stream>>>(n, tau2, 1.0 - tau2, h_i * (tau2 + tau), 0.0, yold, yn, F[0], F[0], ycur);
+        } else {
+          ark::interp_kernel<<<ark::RG, ark::RB, 0, stream>>>(n, -tau, 1.0 + tau, 0.0, 0.0, yold, yn, F[0], F[0], ycur);
+        }
+        std::swap(yn, ycur); // the result vector
+        done = true;
+      }
+    }
+    (void)told_i;
+    if (rc != PRX_OK) {
+      break;
+    }
+    // unflatten with FC = nfe in every cell (ReactorArkode.cpp:237-241); react returns nfe
+    ark::fill_ll_kernel<<<ark::RG, ark::RB, 0, stream>>>(nc, nfe, fcunt);
+    BoxArgs b = a;
+    ARK_CUDA(ops->unflatten(b, h->cfg, 1, yn, rhoe, fcunt, stream));
+    h->ark_last_nfe = nfe;
+    h->ark_nfe += nfe;
+    h->ark_cells += nc;
+  } while (0);
+#undef ARK_CUDA
+  cudaFreeAsync(buf, stream);
+  return rc;
+}
+
 int prx_react_box(
   prx_handle* h, const int lo[3], const int hi[3], const prx_array4* rY, const prx_array4* rYsrc,
   const prx_array4* T, const prx_array4* rE, const prx_array4* rEsrc, const prx_array4* FC,
@@ -571,6 +912,9 @@ int prx_react_box(
   }
   a.dt = dt;
   a.time = time;
+  if (h->cfg.reactor_kind == PRX_REACTOR_ARKODE) {
+    return react_arkode(h, a, (cudaStream_t)cuda_stream); // the mask is ignored, as in the reference (ReactorArkode.cpp:143)
+  }
   return react_args(h, a, (cudaStream_t)cuda_stream);
 }
 
@@ -627,7 +971,8 @@ static int react_state_one(
   }
   a.dt = dt;
   a.time = 0.0; // React.cpp:171: current_time = 0
-  const bool fused = (h->cfg.reactor_kind == PRX_REACTOR_RK64) || h->ops->bdf_is_fused(h->sched);
+  const bool fused = (h->cfg.reactor_kind == PRX_REACTOR_RK64) ||
+                     (h->cfg.reactor_kind == PRX_REACTOR_CVODE && h->ops->bdf_is_fused(h->sched));
   if (fused) {
     return react_args(h, a, stream);
   }
@@ -661,7 +1006,7 @@ static int react_state_one(
   if (e == cudaSuccess) {
     BoxArgs b = a;
     b.layout = LAYOUT_ARRAY4;
-    rc = react_args(h, b, stream);
+    rc = (h->cfg.reactor_kind == PRX_REACTOR_ARKODE) ? react_arkode(h, b, stream) : react_args(h, b, stream);
     if (rc == PRX_OK) {
       e = h->ops->state_unpack(a, h->cfg, stream);
     }
@@ -889,6 +1234,18 @@ int prx_react_boxes(
     return PRX_OK;
   }
   std::lock_guard<std::mutex> lock(h->host_mutex); // the internal streams / events belong to the handle
+  if (h->cfg.reactor_kind == PRX_REACTOR_ARKODE) {
+    // box-coupled integrations whose step-size controller carries its history from one call to the next (prx_arkode.cuh):
+    // the boxes run one after the other, in the caller's order, on the caller's stream
+    for (int b = 0; b < nboxes; b++) {
+      const int rcb = prx_react_box(h, lo + 3 * b, hi + 3 * b, rY + b, rYsrc + b, T + b, rE + b, rEsrc + b, FC + b,
+                                    mask != nullptr ? mask + b : nullptr, dt, time, cuda_stream);
+      if (rcb != PRX_OK) {
+        return rcb;
+      }
+    }
+    return PRX_OK;
+  }
   int ns = 1;
   {
     // the per-call counters are reset once, on the caller's stream, BEFORE the fan-out event: every box accumulates into them
@@ -953,6 +1310,9 @@ int prx_react_flat(
   }
   if (y == nullptr || ysrc == nullptr || e == nullptr || esrc == nullptr) {
     return fail(h, PRX_ERR_BAD_ARG, "prx_react_flat: null pointer");
+  }
+  if (h->cfg.reactor_kind == PRX_REACTOR_ARKODE) {
+    return fail(h, PRX_ERR_UNSUPPORTED, "prx_react_flat: the 1-D react of ReactorArkode is not implemented (Array4 react only)");
   }
   BoxArgs a;
   std::memset(&a, 0, sizeof(a));
@@ -1295,6 +1655,7 @@ int prx_reset_stats(prx_handle* h)
   DeviceGuard g(h->device);
   PRX_CUDA(h, cudaDeviceSynchronize());
   PRX_CUDA(h, cudaMemset(h->d_stats, 0, sizeof(DevStats)));
+  h->ark_nfe = h->ark_nst = h->ark_netf = h->ark_too_much_work = h->ark_cells = 0;
   return PRX_OK;
 }
 
@@ -1319,6 +1680,13 @@ int prx_get_stats(prx_handle* h, prx_stats* out)
   out->n_failed = (long long)s.v[ST_FAILED];
   out->max_steps = (long long)s.v[ST_MAXSTEPS];
   out->reserved = 0;
+  if (h->cfg.reactor_kind == PRX_REACTOR_ARKODE) { // box-coupled: steps / RHS sweeps / error-test failures of the boxes, summed
+    out->cells = h->ark_cells;
+    out->n_steps = h->ark_nst;
+    out->n_rhs = h->ark_nfe;
+    out->n_errfail = h->ark_netf;
+    out->n_failed = h->ark_too_much_work;
+  }
   return PRX_OK;
 }
 
@@ -1334,6 +1702,9 @@ int prx_last_react_return(prx_handle* h)
   }
   if (h->cfg.reactor_kind == PRX_REACTOR_CVODE && h->last_layout == LAYOUT_ARRAY4) {
     return 20; // ReactorCvode.cpp:1463-1464: "Dummy, the return value is no longer used"
+  }
+  if (h->cfg.reactor_kind == PRX_REACTOR_ARKODE) {
+    return (int)h->ark_last_nfe; // ReactorArkode.cpp:259: return static_cast<int>(nfe)
   }
   DeviceGuard g(h->device);
   if (cudaDeviceSynchronize() != cudaSuccess || h->last_ncells <= 0) {

@@ -2278,6 +2278,55 @@ cudaError_t launch_transport(const PrimArgs& a, cudaStream_t stream)
 cudaError_t launch_transport(const PrimArgs&, cudaStream_t) { return cudaErrorNotSupported; }
 #endif
 
+// ---- ReactorArkode stage (PP/Source/Reactions/ReactorArkode.cpp:385-420 cF_RHS, SUN/src/arkode/arkode_erkstep.c:650-700):
+// ycur = sum_j coef_j F_j + yn (the order N_VLinearCombination adds them), then F_is = f(t, ycur) for every cell.  One thread
+// per cell, CYOrder columns: every read and write is a coalesced row.
+__global__ void __launch_bounds__(PRX_RK_BLOCK, PRX_RK_MINBLOCKS) PRX_CAT(ark_stage_kernel_, PRX_MECH_SUFFIX)(const ArkStageArgs a)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.ncells) {
+    return;
+  }
+  const long long nc = a.ncells;
+  double y[NEQ], yd[NEQ];
+#pragma unroll
+  for (int k = 0; k < NEQ; k++) {
+    const long long o = k * nc + c;
+    if (a.nterms > 0) {
+      double acc = a.coef[0] * a.F[0][o];
+      for (int j = 1; j < a.nterms; j++) {
+        acc += a.coef[j] * a.F[j][o];
+      }
+      acc += 1.0 * a.yn[o];
+      y[k] = acc;
+      a.ycur[o] = acc;
+    } else {
+      y[k] = a.yn[o];
+    }
+  }
+  CellSrc src;
+  src.rhoe_init = a.rhoe[c];
+  src.rhoesrc = a.rhoesrc[c];
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    src.rYsrc[k] = a.rYsrc[k * nc + c];
+  }
+  rhs(a.t, a.reactor_type, y, yd, src);
+#pragma unroll
+  for (int k = 0; k < NEQ; k++) {
+    a.fout[k * nc + c] = yd[k];
+  }
+}
+
+cudaError_t launch_ark_stage(const ArkStageArgs& a, cudaStream_t stream)
+{
+  if (a.ncells <= 0) {
+    return cudaSuccess;
+  }
+  PRX_CAT(ark_stage_kernel_, PRX_MECH_SUFFIX)<<<(a.ncells + PRX_RK_BLOCK - 1) / PRX_RK_BLOCK, PRX_RK_BLOCK, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_state_pack(const BoxArgs& a, cudaStream_t stream)
 {
   if (a.ncells <= 0) {
@@ -2489,6 +2538,9 @@ const char* kernel_name(int reactor_kind, const SchedParams& sp)
   if (reactor_kind == PRX_REACTOR_RK64) {
     return "rk64_kernel_" PRX_STR(PRX_MECH_SUFFIX);
   }
+  if (reactor_kind == PRX_REACTOR_ARKODE) {
+    return "ark_stage_kernel_" PRX_STR(PRX_MECH_SUFFIX);
+  }
   switch (effective_bdf_variant(sp)) {
   case 8:
   case 16:
@@ -2535,7 +2587,7 @@ int bdf_is_fused(const SchedParams& sp) { return effective_bdf_variant(sp) == 0;
 
 const MechOps g_ops = {PRX_NUM_SPECIES, PRX_NUM_REACTIONS, PRX_MECH_NAME, prx_species_names, launch_rk64, launch_bdf, kernel_name, probe_rhs, probe_jac,
                        launch_flatten, launch_unflatten, launch_state_pack, launch_state_unpack, bdf_is_fused, launch_compute_temp,
-                       launch_ctoprim, launch_transport};
+                       launch_ctoprim, launch_transport, launch_ark_stage};
 
 } // namespace
 

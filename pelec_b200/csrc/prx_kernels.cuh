@@ -77,6 +77,22 @@ struct PrimArgs
   double small_num;             // PeleC constants::small_num()
 };
 
+// ---- ReactorArkode (box-coupled explicit Runge-Kutta, prx_api.cu react_arkode): one stage = a linear combination of
+// the stage derivatives + the ODE right-hand side of every cell; vectors are CYOrder columns v[k * ncells + c]
+struct ArkStageArgs
+{
+  int ncells, reactor_type, nterms;
+  double t;
+  double coef[8];
+  const double* F[8];
+  const double* yn;
+  double* ycur; // may be nullptr when nterms == 0 (f at yn itself)
+  double* fout;
+  const double* rhoe;
+  const double* rhoesrc;
+  const double* rYsrc;
+};
+
 // device-side counters (unsigned long long so that atomicAdd applies)
 struct DevStats
 {
@@ -132,6 +148,7 @@ struct MechOps
   cudaError_t (*compute_temp)(const BoxArgs&, cudaStream_t stream); // pc_cmpTemp on a.snew
   cudaError_t (*ctoprim)(const PrimArgs&, cudaStream_t stream);      // pc_ctoprim: u -> q, qa
   cudaError_t (*transport)(const PrimArgs&, cudaStream_t stream);    // SimpleTransport::get_transport_coeffs
+  cudaError_t (*ark_stage)(const ArkStageArgs&, cudaStream_t stream); // ReactorArkode: stage state + cF_RHS
 };
 
 // one per kernel translation unit of this build (gen/mech_registry.inc, written by the Makefile from MECHS)

@@ -20,7 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PRX_LIB_PATH") or os.path.join(HERE, "lib", "libpelerx_b200.so")  # override: A/B builds
 
 MECHANISMS = {"LiDryer": 0, "drm19": 1, "dodecane_lu": 2}
-REACTOR_KINDS = {"ReactorRK64": 0, "ReactorCvode": 1}
+REACTOR_KINDS = {"ReactorRK64": 0, "ReactorCvode": 1, "ReactorArkode": 2}
 SOLVE_TYPES = {"denseAJ_direct": 0, "dense_direct": 1}
 # solve types of the reference that this path does not implement (PP ReactorCvode.cpp:507-934)
 UNSUPPORTED_SOLVE_TYPES = ("GMRES", "precGMRES", "sparse_direct", "custom_direct", "magma_direct", "fixed_point")
@@ -42,7 +42,7 @@ class prx_config(C.Structure):
                 ("max_order", C.c_int), ("max_nls_iters", C.c_int), ("solve_type", C.c_int),
                 ("rk64_nsubsteps_guess", C.c_int), ("rk64_nsubsteps_min", C.c_int),
                 ("rk64_nsubsteps_max", C.c_int), ("clean_init_massfrac", C.c_int), ("verbose", C.c_int),
-                ("device", C.c_int)]
+                ("device", C.c_int), ("ark_method", C.c_int), ("ark_controller", C.c_int)]
 
 
 class prx_array4(C.Structure):
@@ -191,7 +191,8 @@ class ReactorB200:
         # ParmParse-style keys with the reference's defaults (ReactorCvode.cpp:18-35, ReactorRK64.cpp:12-18)
         self.parm = {"ode.rtol": 1e-6, "ode.atol": 1e-10, "ode.max_nls_iters": 3, "ode.clean_init_massfrac": 0,
                      "ode.verbose": 0, "cvode.max_order": 2, "cvode.solve_type": "denseAJ_direct",
-                     "ode.rk64_nsubsteps_guess": 10, "ode.rk64_nsubsteps_min": 5, "ode.rk64_nsubsteps_max": 500}
+                     "ode.rk64_nsubsteps_guess": 10, "ode.rk64_nsubsteps_min": 5, "ode.rk64_nsubsteps_max": 500,
+                     "ode.rk_method": 40, "ode.rk_controller": 0}
         for k, v in parm.items():
             k = k.replace("__", ".")
             if k not in self.parm:
@@ -222,6 +223,7 @@ class ReactorB200:
         cfg.clean_init_massfrac = int(self.parm["ode.clean_init_massfrac"])
         cfg.verbose = int(self.parm["ode.verbose"])
         cfg.device = int(device)
+        cfg.ark_method, cfg.ark_controller = int(self.parm["ode.rk_method"]), int(self.parm["ode.rk_controller"])
         h = C.c_void_p()
         rc = self.lib.prx_create(C.byref(cfg), C.byref(h))
         if rc != PRX_OK:

@@ -1,0 +1,63 @@
+"""ReactorArkode (PP/Source/Reactions/ReactorArkode.cpp:135-260, the ERKStep default) behind the C ABI: the box-coupled adaptive
+explicit Runge-Kutta integration of ARKODE - one step size and one WRMS error norm for the whole box, PID / PI controller whose
+history carries over from one react call to the next, Hermite interpolation back to tout - restated for the GPU
+(pelec_b200/csrc/prx_arkode.cuh).  Fixtures: three successive calls of one reference reactor object on three different boxes
+(tests/golden/make_golden5.py, unmodified reference).
+
+Bar: the step-size sequence depends on box-wide norms that are summed in a different order on the device, so results agree to
+rounding-amplified-by-the-controller rather than bit for bit: |d rhoY_k| <= 1e-5 * (atol + rtol |rhoY_k|) (measured: 1e-7 of the
+integrator's own tolerance), |dT| / T <= 1e-11, and the SAME number of right-hand-side evaluations (FC, react's return value) -
+i.e. the same accepted / rejected step sequence."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CASES = {"default": dict(rtol=1e-6, atol=1e-10, rk_method=40, rk_controller=0, typ=False),
+         "bs_pi_typ": dict(rtol=1e-8, atol=1e-10, rk_method=30, rk_controller=1, typ=True)}
+
+
+@pytest.mark.parametrize("mech", ["LiDryer", "drm19"])
+@pytest.mark.parametrize("tag", sorted(CASES))
+def test_arkode_matches_reference_over_successive_calls(mech, tag):
+    from oracle.pyoracle import BoxState
+    from pelec_b200.reactor import ReactorB200
+    z = np.load(os.path.join(GOLD, "arkode_%s.npz" % mech))
+    kw = CASES[tag]
+    dt = float(z["dt"])
+    r = ReactorB200.create("ReactorArkode", mech, ode__rtol=kw["rtol"], ode__atol=kw["atol"], ode__rk_method=kw["rk_method"],
+                           ode__rk_controller=kw["rk_controller"])
+    r.init(1, 1)
+    N = z[tag + "_0_rY0"].shape[0]
+    if kw["typ"]:
+        r.set_typ_vals_ode(np.concatenate([np.full(N, 1e-4), [2000.0]]))
+    worst = []
+    for i in range(3):
+        pre = "%s_%d_" % (tag, i)
+        s = BoxState(z[pre + "rY0"].copy(), z[pre + "T0"].copy(), z[pre + "rE0"].copy(), z[pre + "rYsrc"].copy(), z[pre + "rEsrc"].copy())
+        ret = r.react_host(s.ncells, 1, 1, s.rY, s.rYsrc, s.T, s.rE, s.rEsrc, s.FC, s.mask, dt, 0.0)
+        nfe = int(z[tag + "_nfe"][i])
+        lim = kw["atol"] + kw["rtol"] * np.abs(z[pre + "rY"])
+        dy = float((np.abs(s.rY - z[pre + "rY"]) / lim).max())
+        dT = float((np.abs(s.T - z[pre + "T"]) / z[pre + "T"]).max())
+        worst.append((dy, dT, int(s.FC[0]), nfe))
+        assert np.all(s.FC == s.FC[0]) and np.array_equal(z[pre + "FC"], np.full(s.ncells, float(nfe)))
+        assert int(s.FC[0]) == nfe, worst          # same accepted / rejected step sequence
+        assert r.last_react_return() == nfe
+        assert dy <= 1e-5 and dT <= 1e-11, worst
+        assert np.array_equal(s.rE, z[pre + "rE"])  # rho*e advances by dt * source exactly (box_unflatten)
+        del ret
+    print("arkode %s %s: (|d rhoY| / tol, |dT|/T, FC, nfe) per call: %s" % (mech, tag, worst))
+    r.close()
+
+
+def test_arkode_unsupported_options_fail_loudly():
+    from pelec_b200.reactor import PrxError, ReactorB200
+    r = ReactorB200.create("ReactorArkode", "LiDryer", ode__rk_method=52)  # Dormand-Prince: table not carried
+    with pytest.raises(PrxError):
+        r.init(1, 1)
+    r = ReactorB200.create("ReactorArkode", "LiDryer", ode__rk_controller=3)  # explicit Gustafsson
+    with pytest.raises(PrxError):
+        r.init(1, 1)

@@ -33,6 +33,9 @@ CASES = [
     # (stock integrator, stock build is CUDA, our integrator, our build is CUDA, bar on the state)
     ("ReactorCvode", False, "ReactorCvodeB200", False, 1e-7),
     ("ReactorRK64", False, "ReactorRK64B200", False, 1e-9),
+    # the reference's third reactor (the CI regression case pmf-lidryer-arkode): box-coupled ERKStep, controller history carried
+    # from box to box in MFIter order
+    ("ReactorArkode", False, "ReactorArkodeB200", False, 1e-9),
     # the CUDA build of the application (AMReX + PeleC + PelePhysics compiled by nvcc for sm_100a, state in device
     # memory): the shim's AMREX_USE_GPU branch hands PeleC's device FABs and AMReX's stream to prx_react_box.  ReactorCvode is
     # compared with the CPU build's per-cell ReactorCvode (the GPU ReactorCvode of the reference integrates each box as one

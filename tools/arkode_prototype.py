@@ -1,0 +1,129 @@
+"""TEST INFRASTRUCTURE: numpy prototype of the ARKODE ERKStep control logic restated in pelec_b200/csrc/prx_arkode.cuh + prx_api.cu
+(react_arkode), with the RHS of the pinned C oracle - used on the CPU to debug the port against the reference fixture
+(tests/golden/arkode_<mech>.npz): python tools/arkode_prototype.py LiDryer default  ->  per call nfe (ref nfe), steps, error-test
+failures, deviation in units of the tolerance.  It reproduces the reference RHS-evaluation counts of all twelve fixture calls."""
+import sys, os
+sys.path.insert(0, '/root/repo')
+import numpy as np
+from oracle.pyoracle import Oracle, Reference, reacteval_states, BoxState
+
+def table(method):
+    if method == 40:
+        s=5; A=np.zeros((5,5)); A[1,0]=.5; A[2,1]=.5; A[3,2]=1.; A[4,0]=5/32; A[4,1]=7/32; A[4,2]=13/32; A[4,3]=-1/32
+        b=np.array([1/6,1/3,1/3,1/6,0.]); d=np.array([-1/2,7/3,7/3,13/6,-16/3]); c=np.array([0,.5,.5,1.,.75]); q,p=4,3
+    else:
+        s=4; A=np.zeros((4,4)); A[1,0]=.5; A[2,1]=.75; A[3,0]=2/9; A[3,1]=1/3; A[3,2]=4/9
+        b=np.array([2/9,1/3,4/9,0.]); d=np.array([7/24,1/4,1/3,1/8]); c=np.array([0,.5,.75,1.]); q,p=3,2
+    return s,A,b,d,c,q,p
+
+class Ctl:
+    def __init__(s, kind):
+        s.k1,s.k2,s.k3=(0.58,-0.21,0.1) if kind==0 else ((0.8,-0.31,0.0) if kind==1 else (1.0,0,0))
+        s.bias=1.5; s.ep=s.epp=s.hp=s.hpp=1.0; s.first=0
+    def est(s,h,p,dsm):
+        o=p+1; e1=max(s.bias*dsm,1e-10); e2=max(s.ep,1e-10); e3=max(s.epp,1e-10)
+        if s.first<1: return h*e1**(-s.k1/o)
+        if s.first<2: return h*e1**(-s.k1/o)*e2**(-s.k2/o)
+        return h*e1**(-s.k1/o)*e2**(-s.k2/o)*e3**(-s.k3/o)
+    def upd(s,h,dsm):
+        s.epp=s.ep; s.ep=s.bias*dsm; s.hpp=s.hp; s.hp=h
+        if s.first<2: s.first+=1
+
+def arkode_box(orc, st, dt, ctl, rtol, atol, method, typ=None, log=None):
+    N=orc.N; nc=st.ncells; neq=N+1
+    s,A,b,d,c,q,p=table(method)
+    rho=st.rY.sum(axis=0); Y=(st.rY/rho).T.copy()
+    T0=orc.ey2t(st.rE/rho, Y, st.T)
+    yn=np.concatenate([st.rY.T, T0[:,None]],axis=1).copy()   # [nc, neq]
+    atolv=np.full(neq, atol) if typ is None else typ*atol
+    nfe=[0]
+    def f(t,y):
+        nfe[0]+=1
+        return orc.fkernelspec(t, np.ascontiguousarray(y), st.rE, st.rEsrc, np.ascontiguousarray(st.rYsrc.T))
+    wr=lambda v,w: np.sqrt(np.sum((v*w)**2)/v.size)
+    ewt=1.0/(rtol*np.abs(yn)+atolv[None,:])
+    ur=2.220446049250313e-16
+    t0=0.0; tout=dt; tn=tcur=t0
+    tdist=abs(tout-tcur); tround=ur*max(abs(tcur),abs(tout))
+    F=[None]*s
+    F[0]=f(tn,yn)
+    hlb=100*tround
+    hub_inv=np.max(np.abs(F[0])/(0.1*np.abs(yn)+1.0/ewt)); hub=0.1*tdist
+    if hub*hub_inv>1: hub=1/hub_inv
+    hg=np.sqrt(hlb*hub)
+    if hub<hlb: h=hg
+    else:
+        for c1 in range(1,5):
+            ycur=hg*F[0]+yn; f1=f(tcur+hg,ycur); ydd=wr((1/hg)*f1+(-1/hg)*F[0], ewt)
+            hnew=np.sqrt(2/ydd) if ydd*hub*hub>2 else np.sqrt(hg*hub)
+            if c1==4: break
+            hrat=hnew/hg
+            if 0.5<hrat<2: break
+            if c1>1 and hrat>2: hnew=hg; break
+            hg=hnew
+        h=min(max(0.5*hnew,hlb),hub)
+    etamax=10000.; eta=1.; hprime=h; init=True; fcur=True; nst=0; nloc=0; netf=0
+    stiff=np.allclose(b[:s],A[s-1,:s],atol=1e-14)
+    while True:
+        if not init: ewt=1.0/(rtol*np.abs(yn)+atolv[None,:])
+        if nloc>=500: break
+        if ur*wr(yn,ewt)>1: break
+        if hprime!=h: h=h*eta
+        nef=0; ok=False
+        while True:
+            if not fcur:
+                F[0]=F[s-1].copy() if stiff else f(tn,yn); fcur=True
+            for i in range(1,s):
+                yc=None
+                for j in range(i):
+                    if A[i,j]!=0:
+                        yc=(h*A[i,j])*F[j] if yc is None else yc+(h*A[i,j])*F[j]
+                yc=yc+yn
+                F[i]=f(tn+c[i]*h,yc)
+            ynew=None; ye=None
+            for j in range(s):
+                ynew=(h*b[j])*F[j] if ynew is None else ynew+(h*b[j])*F[j]
+                ye=(h*(b[j]-d[j]))*F[j] if ye is None else ye+(h*(b[j]-d[j]))*F[j]
+            ynew=ynew+yn
+            dsm=wr(ye,ewt)
+            hacc=ctl.est(h,p-1,dsm); hacc*=0.99
+            hacc=min(abs(hacc),abs(etamax*h)); hacc=max(hacc,0.1*h)
+            if dsm<=1 and (hacc>h*0.999999 and hacc<h*1.5*1.000001): hacc=h
+            eta=hacc/h; eta=min(eta,etamax)
+            if log is not None: log.append((tn,h,dsm,eta))
+            if dsm<=1: ok=True; break
+            nef+=1; netf+=1
+            if nef==7: break
+            etamax=1.0
+            if nef>=2: eta=min(eta,0.3)
+            eta=min(eta,etamax)
+            h*=eta; hprime=h
+        if not ok: break
+        tcur=tn+h; yold=yn; fold=F[0]; hi=h
+        yn=ynew; fcur=False; ctl.upd(h,dsm); nst+=1; tn=tcur; hprime=h*eta; etamax=25.; init=False; nloc+=1
+        if (tcur-tout)*h>=0:
+            tau=(tout-tcur)/h
+            fn=F[s-1].copy() if stiff else f(tn,yn)
+            t2=tau*tau; t3=tau*t2
+            if q-1>=3: yout=(3*t2+2*t3)*yold+(1-3*t2-2*t3)*yn+hi*(t2+t3)*fold+hi*(tau+2*t2+t3)*fn
+            elif q-1==2: yout=t2*yold+(1-t2)*yn+hi*(t2+tau)*fn
+            else: yout=-tau*yold+(1+tau)*yn
+            yn=yout; break
+    return yn, nfe[0], nst, netf
+
+if __name__=="__main__":
+    mech=sys.argv[1]; tag=sys.argv[2]
+    z=np.load('/root/repo/tests/golden/arkode_%s.npz'%mech)
+    os.dup2(os.open(os.devnull,os.O_WRONLY),1)
+    orc=Oracle(mech)
+    kw={"default":dict(rtol=1e-6,atol=1e-10,method=40,kind=0,typ=False),"bs_pi_typ":dict(rtol=1e-8,atol=1e-10,method=30,kind=1,typ=True)}[tag]
+    ctl=Ctl(kw["kind"]); N=orc.N
+    typ=np.concatenate([np.full(N,1e-4),[2000.0]]) if kw["typ"] else None
+    for i in range(3):
+        pre="%s_%d_"%(tag,i)
+        st=BoxState(z[pre+"rY0"].copy(),z[pre+"T0"].copy(),z[pre+"rE0"].copy(),z[pre+"rYsrc"].copy(),z[pre+"rEsrc"].copy())
+        log=[]
+        y,nfe,nst,netf=arkode_box(orc,st,float(z["dt"]),ctl,kw["rtol"],kw["atol"],kw["method"],typ,log)
+        lim=kw["atol"]+kw["rtol"]*np.abs(z[pre+"rY"])
+        dy=np.max(np.abs(y[:,:N].T-z[pre+"rY"])/lim)
+        sys.stderr.write("%s %s call %d: nfe %d (ref %d) nst %d netf %d dy/tol %.3e dT %.2e h0 %.3e\n"%(mech,tag,i,nfe,int(z[tag+"_nfe"][i]),nst,netf,dy,np.max(np.abs(y[:,N]-z[pre+"T"])/z[pre+"T"]),log[0][1]))

@@ -26,7 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mech", default="LiDryer")
     ap.add_argument("--n", type=int, default=64)
-    ap.add_argument("--reactor", default="ReactorCvode", choices=["ReactorCvode", "ReactorRK64", "ReactorCvodeB200", "ReactorRK64B200"],
+    ap.add_argument("--reactor", default="ReactorCvode", choices=["ReactorCvode", "ReactorRK64", "ReactorArkode", "ReactorCvodeB200", "ReactorRK64B200", "ReactorArkodeB200"],
                     help="...B200: this repo's reactor through the shim's AMREX_USE_GPU branch (device pointers, AMReX's stream)")
     ap.add_argument("--solve-type", default="GMRES")
     ap.add_argument("--rtol", type=float, default=1e-10)
