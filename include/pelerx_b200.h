@@ -54,7 +54,7 @@ typedef enum {
   PRX_REACTOR_RK64 = 0,      /* "ReactorRK64"  PP/Source/Reactions/ReactorRK64.cpp:166-320  */
   PRX_REACTOR_CVODE = 1,     /* "ReactorCvode" PP/Source/Reactions/ReactorCvode.cpp:1267-1489,
                                 per-cell (CPU-branch) semantics: one BDF integration per cell */
-  PRX_REACTOR_ARKODE = 2     /* "ReactorArkode" PP/Source/Reactions/ReactorArkode.cpp:135-260 (ode.use_erkstep = 1, the default):
+  PRX_REACTOR_ARKODE = 2     /* "ReactorArkode" PP/Source/Reactions/ReactorArkode.cpp:135-260 (ode.use_erkstep = 1, the default, or 0):
                                 ARKODE's adaptive explicit Runge-Kutta stepper on the WHOLE BOX as one system - one step
                                 size and one WRMS error norm for all cells of a react call, as the reference does on every
                                 backend; FC = the box's RHS-evaluation count in every cell.  Array4 react only. */
@@ -87,6 +87,9 @@ typedef struct prx_config {
   int ark_method;           /* ode.rk_method (ReactorArkode.cpp:26-88): 40 Zonneveld 5-3-4 (default), 20 Heun-Euler 2-1-2,
                                30 Bogacki-Shampine 4-2-3 */
   int ark_controller;       /* ode.rk_controller (ReactorArkode.cpp:90-116): 0 PID (default), 1 PI, 2 I */
+  int ark_use_erkstep;      /* ode.use_erkstep (ReactorArkode.cpp:13): 1 = ERKStep (default), 0 = ARKStep with the same explicit
+                               table - the same algorithm with ARKODE's generic adaptivity constants (safety 0.96, growth 20)
+                               instead of ERKStep's (0.99, 25) */
 } prx_config;
 
 /* Same fields and meaning as amrex::Array4<T> (AMR/Src/Base/AMReX_Array4.H:60-68):

@@ -116,11 +116,7 @@ int ReactorB200<KIND>::init(int reactor_type, int /*ncells*/)
   cfg.verbose = this->verbose;
   if (KIND == b200::ARKODE) {
     // ReactorArkode.cpp:13-21: ode.use_erkstep (1), ode.rk_method (40), ode.rk_controller (0)
-    int use_erkstep = 1;
-    pp.query("use_erkstep", use_erkstep);
-    if (use_erkstep != 1) {
-      amrex::Abort("ReactorArkodeB200: ode.use_erkstep = 0 (ARKStep with an explicit table) is not implemented; use the ERKStep default");
-    }
+    pp.query("use_erkstep", cfg.ark_use_erkstep);
     pp.query("rk_method", cfg.ark_method);
     pp.query("rk_controller", cfg.ark_controller);
   }

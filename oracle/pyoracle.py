@@ -315,14 +315,15 @@ class Reference:
         self._parm("ode", "verbose", 0)
         return self._react("ReactorRK64", st, dt, time, reactor_type)
 
-    def react_arkode(self, states, dt, time=0.0, rtol=1e-6, atol=1e-10, rk_method=40, rk_controller=0, typ_vals=None, reactor_type=1):
+    def react_arkode(self, states, dt, time=0.0, rtol=1e-6, atol=1e-10, rk_method=40, rk_controller=0, typ_vals=None, reactor_type=1,
+                     use_erkstep=1):
         """ReactorArkode (ERKStep) on a SEQUENCE of boxes with ONE reactor object, as PeleC's MFIter loop does: each state is
         one box (ncells x 1 x 1) integrated as one coupled system; the reactor's step-size controller is created once in init()
         and keeps its history from call to call (ReactorArkode.cpp:90-116, 207).  Returns react()'s ints (nfe per call)."""
         self._parm("ode", "rtol", repr(rtol))
         self._parm("ode", "atol", repr(atol))
         self._parm("ode", "verbose", 0)
-        self._parm("ode", "use_erkstep", 1)
+        self._parm("ode", "use_erkstep", int(use_erkstep))
         self._parm("ode", "rk_method", rk_method)
         self._parm("ode", "rk_controller", rk_controller)
         self._parm("ode", "clean_init_massfrac", 0)

@@ -247,6 +247,7 @@ int prx_default_config(prx_config* cfg)
   cfg->device = -1;
   cfg->ark_method = 40;    // ReactorArkode.H: rk_method{40} = ARKODE_ZONNEVELD_5_3_4
   cfg->ark_controller = 0; // PID
+  cfg->ark_use_erkstep = 1;
   return PRX_OK;
 }
 
@@ -686,6 +687,10 @@ static int react_arkode(prx_handle* h, const BoxArgs& a, cudaStream_t stream)
     if (rc != PRX_OK) {
       break;
     }
+    // ERKStep overrides ARKODE's adaptivity defaults (erkStep_SetDefaults, arkode_erkstep_io.c:310-312: safety 0.99, growth 25);
+    // ARKStep with an explicit table (ode.use_erkstep = 0) runs with ARKODE's own (arkode_adapt_impl.h:41-42: 0.96, 20) -
+    // measured against the reference: the two differ in nothing else
+    const double ark_safety = h->cfg.ark_use_erkstep ? 0.99 : 0.96, ark_growth = h->cfg.ark_use_erkstep ? 25.0 : 20.0;
     double etamax = 10000.0; // etamx1: first step
     double eta = 1.0, hprime = hstep;
     bool initsetup = true, fn_is_current = true;
@@ -774,7 +779,7 @@ static int react_arkode(prx_handle* h, const BoxArgs& a, cudaStream_t stream)
           double h_acc = h->ark_ctl.estimate(hstep, controller_order, dsm);
           const double int_dir = hstep / std::fabs(hstep);
           double h_cfl = 1.0e30 * std::fabs(hstep); // arkExpStab returns 0: no explicit stability limit
-          h_acc *= 0.99; // ERKStep's own safety factor (erkStep_SetDefaults, arkode_erkstep_io.c:311), not ARKODE's 0.96
+          h_acc *= ark_safety;
           h_cfl *= 0.5 * int_dir;
           h_acc = int_dir * std::fmin(std::fabs(h_acc), std::fabs(etamax * hstep));
           h_acc = int_dir * std::fmax(std::fabs(h_acc), std::fabs(0.1 * hstep));
@@ -824,7 +829,7 @@ static int react_arkode(prx_handle* h, const BoxArgs& a, cudaStream_t stream)
       h->ark_nst++;
       tn = tcur;
       hprime = hstep * eta;
-      etamax = 25.0; // ERKStep's growth factor (arkode_erkstep_io.c:312), not ARKODE's 20
+      etamax = ark_growth;
       initsetup = false;
       nstloc++;
       if ((tcur - tout) * hstep >= 0.0) { // ARK_NORMAL: tout reached, interpolate back (ARKodeGetDky)

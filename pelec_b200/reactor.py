@@ -42,7 +42,7 @@ class prx_config(C.Structure):
                 ("max_order", C.c_int), ("max_nls_iters", C.c_int), ("solve_type", C.c_int),
                 ("rk64_nsubsteps_guess", C.c_int), ("rk64_nsubsteps_min", C.c_int),
                 ("rk64_nsubsteps_max", C.c_int), ("clean_init_massfrac", C.c_int), ("verbose", C.c_int),
-                ("device", C.c_int), ("ark_method", C.c_int), ("ark_controller", C.c_int)]
+                ("device", C.c_int), ("ark_method", C.c_int), ("ark_controller", C.c_int), ("ark_use_erkstep", C.c_int)]
 
 
 class prx_array4(C.Structure):
@@ -192,7 +192,7 @@ class ReactorB200:
         self.parm = {"ode.rtol": 1e-6, "ode.atol": 1e-10, "ode.max_nls_iters": 3, "ode.clean_init_massfrac": 0,
                      "ode.verbose": 0, "cvode.max_order": 2, "cvode.solve_type": "denseAJ_direct",
                      "ode.rk64_nsubsteps_guess": 10, "ode.rk64_nsubsteps_min": 5, "ode.rk64_nsubsteps_max": 500,
-                     "ode.rk_method": 40, "ode.rk_controller": 0}
+                     "ode.rk_method": 40, "ode.rk_controller": 0, "ode.use_erkstep": 1}
         for k, v in parm.items():
             k = k.replace("__", ".")
             if k not in self.parm:
@@ -224,6 +224,7 @@ class ReactorB200:
         cfg.verbose = int(self.parm["ode.verbose"])
         cfg.device = int(device)
         cfg.ark_method, cfg.ark_controller = int(self.parm["ode.rk_method"]), int(self.parm["ode.rk_controller"])
+        cfg.ark_use_erkstep = int(self.parm["ode.use_erkstep"])
         h = C.c_void_p()
         rc = self.lib.prx_create(C.byref(cfg), C.byref(h))
         if rc != PRX_OK:

@@ -3,7 +3,7 @@
 the build container only): three successive react calls of ONE reactor object on three different boxes (each a coupled system
 of 48 / 64 / 32 cells; ReactEval states, flame-table states, ReactEval states again) - the step-size controller carries its
 history across the calls - for the default configuration (ERKStep, Zonneveld 5-3-4, PID, rtol 1e-6, atol 1e-10) and for
-Bogacki-Shampine 4-2-3 with the PI controller and typical values."""
+Bogacki-Shampine 4-2-3 with the PI controller and typical values, and for ode.use_erkstep = 0 (ARKStep, explicit table)."""
 import os
 import sys
 
@@ -38,7 +38,8 @@ def main():
         out = {}
         for tag, kw in (("default", dict(rtol=1e-6, atol=1e-10, rk_method=40, rk_controller=0)),
                         ("bs_pi_typ", dict(rtol=1e-8, atol=1e-10, rk_method=30, rk_controller=1,
-                                           typ_vals=np.concatenate([np.full(ref.N, 1e-4), [2000.0]])))):
+                                           typ_vals=np.concatenate([np.full(ref.N, 1e-4), [2000.0]]))),
+                        ("arkstep", dict(rtol=1e-6, atol=1e-10, rk_method=40, rk_controller=0, use_erkstep=0))):
             sts = boxes(ref, mech)
             ins = [s.copy() for s in sts]
             nfe = ref.react_arkode(sts, DT, **kw)

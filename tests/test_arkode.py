@@ -16,7 +16,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 CASES = {"default": dict(rtol=1e-6, atol=1e-10, rk_method=40, rk_controller=0, typ=False),
-         "bs_pi_typ": dict(rtol=1e-8, atol=1e-10, rk_method=30, rk_controller=1, typ=True)}
+         "bs_pi_typ": dict(rtol=1e-8, atol=1e-10, rk_method=30, rk_controller=1, typ=True),
+         "arkstep": dict(rtol=1e-6, atol=1e-10, rk_method=40, rk_controller=0, typ=False, use_erkstep=0)}
 
 
 @pytest.mark.parametrize("mech", ["LiDryer", "drm19"])
@@ -28,7 +29,7 @@ def test_arkode_matches_reference_over_successive_calls(mech, tag):
     kw = CASES[tag]
     dt = float(z["dt"])
     r = ReactorB200.create("ReactorArkode", mech, ode__rtol=kw["rtol"], ode__atol=kw["atol"], ode__rk_method=kw["rk_method"],
-                           ode__rk_controller=kw["rk_controller"])
+                           ode__rk_controller=kw["rk_controller"], ode__use_erkstep=kw.get("use_erkstep", 1))
     r.init(1, 1)
     N = z[tag + "_0_rY0"].shape[0]
     if kw["typ"]:
