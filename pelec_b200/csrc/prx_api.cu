@@ -746,7 +746,7 @@ static int react_arkode(prx_handle* h, const BoxArgs& a, cudaStream_t stream)
             }
           }
           s.yn = yn;
-          s.ycur = ycur;
+          s.ycur = nullptr; // N_VLinearCombination writes ark_mem->ycur; nothing reads it before the next stage overwrites it
           s.fout = F[is];
           s.rhoe = rhoe;
           s.rhoesrc = rhoesrc;

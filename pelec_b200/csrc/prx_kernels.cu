@@ -2299,7 +2299,9 @@ __global__ void __launch_bounds__(PRX_RK_BLOCK, PRX_RK_MINBLOCKS) PRX_CAT(ark_st
       }
       acc += 1.0 * a.yn[o];
       y[k] = acc;
-      a.ycur[o] = acc;
+      if (a.ycur != nullptr) { // the stage state is only needed here, in registers
+        a.ycur[o] = acc;
+      }
     } else {
       y[k] = a.yn[o];
     }
