@@ -37,6 +37,7 @@ struct prx_handle
   size_t d_stage_bytes;
   cudaStream_t stage_stream;
   cudaStream_t in_stream, out_stream; // host staging pipeline of prx_react_box_host: H2D | react | D2H per slab
+  cudaStream_t host_react_streams[3] = {nullptr, nullptr, nullptr}; // extra react streams of that pipeline (slab s reacts on stream s mod n: the drain of one slab's persistent kernel overlaps the next slab's start)
   bool keep_last_steps;              // react_args: do not reset the per-call step sum (slabs of one call)
   ark::Controller ark_ctl;           // ReactorArkode: the step-size controller's history persists across react calls
   ark::Table ark_tab;                //                the Butcher table of cfg.ark_method
@@ -397,6 +398,11 @@ int prx_destroy(prx_handle* h)
   }
   if (h->in_stream) {
     cudaStreamDestroy(h->in_stream);
+  }
+  for (int i = 0; i < 3; i++) {
+    if (h->host_react_streams[i]) {
+      cudaStreamDestroy(h->host_react_streams[i]);
+    }
   }
   if (h->out_stream) {
     cudaStreamDestroy(h->out_stream);
@@ -1367,11 +1373,13 @@ int prx_react_box_host(
   double* d_rEsrc = d_rE + nc;
   double* d_FC = d_rEsrc + nc;
   int* d_mask = reinterpret_cast<int*>(d_FC + nc);
-  // Slab pipeline: the box is cut along k into slabs (PRX_HOST_SLABS, default 2: measured best of 1..12); slab s+1 is copied in while slab s reacts and slab
-  // s-1 is copied out (three streams, full-duplex PCIe).  Every array is SoA with component stride nc, so one slab
+  // Slab pipeline: the box is cut along k into slabs (PRX_HOST_SLABS, default 8); slab s+1 is copied in while slab s reacts
+  // and slab s-1 is copied out (copy-in, copy-out and PRX_HOST_REACT_STREAMS react streams, full-duplex PCIe).  Measured
+  // (r02ae, 128^3 LiDryer, device-timed 67.1 ms): one react stream 2 slabs 75.6 ms / 4 slabs 82.3 ms (every slab's persistent
+  // kernel drains alone); two react streams 2 / 4 / 8 / 12 slabs 73.2 / 71.8 / 70.9 / 70.5 ms.  Every array is SoA with component stride nc, so one slab
   // of one array is a 2-D copy: rows = components (pitch nc), row length = the slab's cells.
   const long long plane = (long long)nx * ny;
-  int nslab = (nz >= 8 && nc >= (1LL << 18)) ? env_int("PRX_HOST_SLABS", 2) : 1;
+  int nslab = (nz >= 8 && nc >= (1LL << 18)) ? env_int("PRX_HOST_SLABS", 8) : 1;
   nslab = nslab < 1 ? 1 : (nslab > 14 ? 14 : nslab);
   nslab = nslab > nz ? nz : nslab;
   // Slab boundaries along k.  What the pipeline cannot hide is the H2D of the FIRST slab and the D2H of the LAST one, so
@@ -1443,8 +1451,34 @@ int prx_react_box_host(
       rc_react = fail(h, PRX_ERR_CUDA, #call, e_);             \
     }                                                          \
   } while (0)
-  h->keep_last_steps = false;
+  // React streams: slab s reacts on stream s mod nrs.  The integrator kernels are persistent (blocks leave only when the
+  // work queue is empty and their last cells have finished), so on ONE stream every slab pays its own drain; on alternating
+  // streams the next slab's blocks move in as the previous slab's leave, and thinner slabs (less exposed first-slab H2D /
+  // last-slab D2H) stop costing kernel efficiency.  PRX_HOST_REACT_STREAMS (1-4, default 2).
+  int nrs = env_int("PRX_HOST_REACT_STREAMS", 2);
+  nrs = nrs < 1 ? 1 : (nrs > 4 ? 4 : nrs);
+  nrs = nrs > nslab ? nslab : nrs;
+  cudaStream_t rs[4] = {st, nullptr, nullptr, nullptr};
+  for (int i = 1; i < nrs; i++) {
+    if (h->host_react_streams[i - 1] == nullptr) {
+      SLAB_CUDA(cudaStreamCreateWithFlags(&h->host_react_streams[i - 1], cudaStreamNonBlocking));
+    }
+    rs[i] = h->host_react_streams[i - 1];
+  }
+  // the per-call step sum is reset once, on the first react stream, before any slab's kernel may add to it
+  h->keep_last_steps = true;
+  h->last_ncells = 0;
+  cudaEvent_t ev_reset = nullptr;
+  SLAB_CUDA(cudaMemsetAsync(&h->d_stats->v[ST_LAST_STEPS], 0, 2 * sizeof(unsigned long long), st));
+  if (nrs > 1) {
+    SLAB_CUDA(cudaEventCreateWithFlags(&ev_reset, cudaEventDisableTiming));
+    SLAB_CUDA(cudaEventRecord(ev_reset, st));
+    for (int i = 1; i < nrs && rc_react == PRX_OK; i++) {
+      SLAB_CUDA(cudaStreamWaitEvent(rs[i], ev_reset, 0));
+    }
+  }
   for (int sidx = 0; sidx < nslab && rc_react == PRX_OK; sidx++) {
+    cudaStream_t st = rs[sidx % nrs];
     const int k0 = kcut[sidx], k1 = kcut[sidx + 1];
     const long long off = plane * k0, cells = plane * (k1 - k0);
     SLAB_CUDA(copy2d(d_rY, rY, sizeof(double), off, cells, N, cudaMemcpyHostToDevice, h->in_stream));
@@ -1460,7 +1494,6 @@ int prx_react_box_host(
     const int lo[3] = {0, 0, k0};
     const int hi[3] = {nx - 1, ny - 1, k1 - 1};
     rc_react = prx_react_box(h, lo, hi, &a_rY, &a_rYsrc, &a_T, &a_rE, &a_rEsrc, &a_FC, &a_mask, dt, time, st);
-    h->keep_last_steps = true; // the following slabs belong to the same react call
     if (rc_react != PRX_OK) {
       break;
     }
@@ -1475,7 +1508,16 @@ int prx_react_box_host(
   h->keep_last_steps = false;
   cudaError_t es = cudaStreamSynchronize(h->out_stream);
   cudaError_t es2 = cudaStreamSynchronize(st);
+  for (int i = 1; i < nrs; i++) {
+    if (rs[i] != nullptr) {
+      const cudaError_t er = cudaStreamSynchronize(rs[i]);
+      es2 = (es2 == cudaSuccess) ? er : es2;
+    }
+  }
   cudaError_t es3 = cudaStreamSynchronize(h->in_stream);
+  if (ev_reset != nullptr) {
+    cudaEventDestroy(ev_reset);
+  }
   for (int sidx = 0; sidx < nslab; sidx++) {
     cudaEventDestroy(ev_in[sidx]);
     cudaEventDestroy(ev_done[sidx]);

@@ -211,8 +211,25 @@ struct CellSrc
   double rYsrc[N];
 };
 
+// The same constants with the species source as a COLUMN of the block's shared memory (element k at p[k * STRIDE],
+// STRIDE = threads per block: conflict-free).  The RHS reads rYsrc at its very end, 40 times per cell, from thread-local
+// memory that has left L1 by then (ncu r02i: 6.6 % of the gen-1 BDF kernel's stall samples sit on that line); the first
+// generation's blocks use no shared memory otherwise.
+template <int STRIDE>
+struct CellSrcCol
+{
+  double rhoe_init;
+  double rhoesrc;
+  struct Col
+  {
+    double* p;
+    PRX_MEM double& operator[](const int i) const { return p[i * STRIDE]; }
+  } rYsrc;
+};
+
 // ODE right-hand side for one cell: y = (rhoY_0..rhoY_{N-1}, T) -> ydot.
-PRX_DEV void rhs(const double t, const int reactor_type, const double* y, double* ydot, const CellSrc& c)
+template <class SrcT>
+PRX_DEV void rhs(const double t, const int reactor_type, const double* y, double* ydot, const SrcT& c)
 {
   double rho = 0.0;
   double Y[N];

@@ -250,8 +250,9 @@ __device__ __forceinline__ void state_unpack(
 // ---- boundary loads / stores ---------------------------------------------------------
 // Array4: SoA, consecutive lanes <-> consecutive i: every component load is a coalesced
 // 256-byte warp transaction.  Flat (YCOrder): cell-major, used by the 1-D react() only.
+template <class SrcT>
 __device__ __forceinline__ bool load_cell(
-  const BoxArgs& a, const int c, double* y /*NEQ*/, CellSrc& src, const int clean_init_massfrac)
+  const BoxArgs& a, const int c, double* y /*NEQ*/, SrcT& src, const int clean_init_massfrac)
 {
   if (a.layout == LAYOUT_ARRAY4) {
     if (a.mask.p != nullptr) {
@@ -317,8 +318,9 @@ __device__ __forceinline__ void store_masked(const BoxArgs& a, const int c)
 }
 
 // box_unflatten (ReactorUtils.H:222-291) / RK64 write-back (ReactorRK64.cpp:290-309)
+template <class SrcT>
 __device__ __forceinline__ void store_cell(
-  const BoxArgs& a, const int c, const double* y /*NEQ: rhoY_new, T (pre re-solve)*/, const CellSrc& src,
+  const BoxArgs& a, const int c, const double* y /*NEQ: rhoY_new, T (pre re-solve)*/, const SrcT& src,
   const int reactor_type, const double fc, const int clean_init_massfrac, const bool resolve_T)
 {
   const double rhoe_out = src.rhoe_init + a.dt * src.rhoesrc;
@@ -500,6 +502,9 @@ __device__ __forceinline__ double* bdf_vec(BdfCell& s, const int sel)
 #else
 #define PRX_HAVE_BDF1 (PRX_NUM_SPECIES <= 32)
 #endif
+#ifndef PRX_SMEM_SRC
+#define PRX_SMEM_SRC 0
+#endif
 #if PRX_HAVE_BDF1
 #ifndef PRX_OUTLINE
 #define PRX_OUTLINE 0 // bit 0: Jacobian out of line, bit 1: RHS out of line (separate register allocation, fewer spills in the loop)
@@ -520,7 +525,14 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
   const BoxArgs a, const BdfParams p, const SchedParams sp, int* __restrict__ queue,
   DevStats* __restrict__ stats)
 {
+#if PRX_SMEM_SRC
+  // the cell's external species source in a shared-memory column (see CellSrcCol)
+  __shared__ double src_col[N * PRX_BLOCK];
+  BdfCellT<BdfStoreLocal, CellSrcCol<PRX_BLOCK>> s;
+  s.src.rYsrc.p = src_col + threadIdx.x;
+#else
   BdfCell s;
+#endif
   int cell = -1;
   bool exhausted = false;
   int req = REQ_NONE;
