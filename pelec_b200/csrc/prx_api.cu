@@ -436,7 +436,7 @@ const char* prx_last_error(const prx_handle* h) { return h ? h->err : "null hand
 // what keeps one-cell-per-thread integrators converged on flame-like fields where neighbours in index space
 // are unrelated (bench.py --states pmf: 319 -> see profiles/README.md).  Each cell's arithmetic does not depend
 // on the order.  Key = T as float; stable radix sort (cub), so equal temperatures keep index order.
-__global__ void order_keys_kernel(const BoxArgs a, const int neq, float* __restrict__ keys, int* __restrict__ idx)
+__global__ void order_keys_kernel(const BoxArgs a, const int neq, const float sign, float* __restrict__ keys, int* __restrict__ idx)
 {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.ncells) {
@@ -458,12 +458,12 @@ __global__ void order_keys_kernel(const BoxArgs a, const int neq, float* __restr
   } else {
     T = a.y[(long long)c * neq + (neq - 1)];
   }
-  keys[c] = (float)T;
+  keys[c] = sign * (float)T; // sign = -1: hottest cells first (PRX_SORT_CELLS=2)
   idx[c] = c;
 }
 
 // returns a stream-ordered allocation holding [order | scratch]; the caller frees it (cudaFreeAsync) after the launch
-static cudaError_t build_order(const BoxArgs& a, int neq, cudaStream_t stream, void** block_out, const int** order_out)
+static cudaError_t build_order(const BoxArgs& a, int neq, bool descending, cudaStream_t stream, void** block_out, const int** order_out)
 {
   const size_t n = (size_t)a.ncells;
   size_t temp_bytes = 0;
@@ -483,7 +483,7 @@ static cudaError_t build_order(const BoxArgs& a, int neq, cudaStream_t stream, v
   float* keys_in = (float*)(block + off_keys_in);
   float* keys_out = (float*)(block + off_keys_out);
   int* idx_in = (int*)(block + off_idx_in);
-  order_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a, neq, keys_in, idx_in);
+  order_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a, neq, descending ? -1.0f : 1.0f, keys_in, idx_in);
   e = cudaGetLastError();
   if (e == cudaSuccess) {
     e = cub::DeviceRadixSort::SortPairs(block + off_temp, temp_bytes, keys_in, keys_out, idx_in, order, (int)n, 0, 32, stream);
@@ -520,7 +520,7 @@ static int react_args(prx_handle* h, const BoxArgs& a, cudaStream_t stream)
   void* order_block = nullptr;
   b.order = nullptr;
   if (h->sched.sort_cells && a.ncells >= 4096) {
-    e = build_order(a, h->ops->num_species + 1, stream, &order_block, &b.order);
+    e = build_order(a, h->ops->num_species + 1, h->sched.sort_cells == 2, stream, &order_block, &b.order);
     if (e != cudaSuccess) {
       return fail(h, PRX_ERR_CUDA, "cell ordering", e);
     }

@@ -297,6 +297,43 @@ struct BdfStoreLocal : public SerialOwner
   PRX_MEM void getrs(MA a, const int* p, VB b);
 };
 
+// The first generation's thread-local store with the vectors every Newton iteration reads (LEVEL >= 2: ewt, LEVEL >= 3: + acor)
+// moved to shared-memory COLUMNS (element i at hot[i * STRIDE], STRIDE = threads per block): the block's otherwise unused
+// shared memory holds what it can of the hot state at the first generation's occupancy; everything else stays in L1/L2-backed
+// local memory.  LEVEL 1 is BdfStoreLocal (only the external source lives in shared memory, see CellSrcCol).
+template <int STRIDE, int LEVEL>
+struct BdfStoreLocalHot : public SerialOwner
+{
+  typedef double* Vec;
+  typedef double* Mat;
+  typedef SVecT<STRIDE> HVec;
+  typedef typename std::conditional<(LEVEL >= 2), HVec, double*>::type EwtVec;
+  typedef typename std::conditional<(LEVEL >= 3), HVec, double*>::type AcorVec;
+  double* hot; // this thread's column: [ewt NEQ][acor NEQ]
+  double zn_[LMAX][NEQ], tempv_[NEQ], ftemp_[NEQ], y_[NEQ], delta_[NEQ];
+  double ewt_[(LEVEL >= 2) ? 1 : NEQ], acor_[(LEVEL >= 3) ? 1 : NEQ];
+  double A_[NEQ * NEQ], savedJ_[NEQ * NEQ];
+  int piv_[NEQ], perm_[NEQ];
+  static PRX_HD int hot_doubles() { return ((LEVEL >= 2) ? NEQ : 0) + ((LEVEL >= 3) ? NEQ : 0); }
+  PRX_MEM int* perm() { return perm_; }
+  PRX_MEM Vec zn(const int j) { return zn_[j]; }
+  PRX_MEM HVec ewt(std::true_type) { return HVec{hot}; }
+  PRX_MEM double* ewt(std::false_type) { return ewt_; }
+  PRX_MEM EwtVec ewt() { return ewt(std::integral_constant<bool, (LEVEL >= 2)>()); }
+  PRX_MEM HVec acor(std::true_type) { return HVec{hot + NEQ * STRIDE}; }
+  PRX_MEM double* acor(std::false_type) { return acor_; }
+  PRX_MEM AcorVec acor() { return acor(std::integral_constant<bool, (LEVEL >= 3)>()); }
+  PRX_MEM Vec tempv() { return tempv_; }
+  PRX_MEM Vec ftemp() { return ftemp_; }
+  PRX_MEM Vec y() { return y_; }
+  PRX_MEM Vec delta() { return delta_; }
+  PRX_MEM Mat A() { return A_; }
+  PRX_MEM double* savedJ() { return savedJ_; }
+  PRX_MEM int* piv() { return piv_; }
+  template <class MA, class VB>
+  PRX_MEM void getrs(MA a, const int* p, VB b);
+};
+
 template <int STRIDE, bool A_SMEM>
 struct BdfStoreSmem : public SerialOwner
 {
@@ -998,6 +1035,17 @@ PRX_MEM void BdfStoreLocal::getrs(MA a, const int* p, VB b)
 #endif
   dense_getrs(a, p, b);
 }
+template <int STRIDE, int LEVEL>
+template <class MA, class VB>
+PRX_MEM void BdfStoreLocalHot<STRIDE, LEVEL>::getrs(MA a, const int* p, VB b)
+{
+  if (NEQ <= 24) {
+    dense_getrs_small(a, p, b, perm_);
+    return;
+  }
+  dense_getrs(a, p, b);
+}
+
 template <int STRIDE, bool A_SMEM>
 template <class MA, class VB>
 PRX_MEM void BdfStoreSmem<STRIDE, A_SMEM>::getrs(MA a, const int* p, VB b)

@@ -505,6 +505,9 @@ __device__ __forceinline__ double* bdf_vec(BdfCell& s, const int sel)
 #ifndef PRX_SMEM_SRC
 #define PRX_SMEM_SRC 0
 #endif
+extern __shared__ double prx_dyn_smem[];
+constexpr int PRX_BDF1_SMEM_BYTES =
+  PRX_SMEM_SRC ? (PRX_NUM_SPECIES + ((PRX_SMEM_SRC >= 2) ? PRX_NUM_SPECIES + 1 : 0) + ((PRX_SMEM_SRC >= 3) ? PRX_NUM_SPECIES + 1 : 0)) * PRX_BLOCK * 8 : 0;
 #if PRX_HAVE_BDF1
 #ifndef PRX_OUTLINE
 #define PRX_OUTLINE 0 // bit 0: Jacobian out of line, bit 1: RHS out of line (separate register allocation, fewer spills in the loop)
@@ -526,10 +529,11 @@ __global__ void __launch_bounds__(PRX_BLOCK, PRX_MINBLOCKS) PRX_CAT(bdf_kernel_,
   DevStats* __restrict__ stats)
 {
 #if PRX_SMEM_SRC
-  // the cell's external species source in a shared-memory column (see CellSrcCol)
-  __shared__ double src_col[N * PRX_BLOCK];
-  BdfCellT<BdfStoreLocal, CellSrcCol<PRX_BLOCK>> s;
-  s.src.rYsrc.p = src_col + threadIdx.x;
+  // the cell's external species source (and, PRX_SMEM_SRC >= 2 / 3, ewt / acor) in shared-memory columns (CellSrcCol,
+  // BdfStoreLocalHot): [rYsrc N][ewt NEQ][acor NEQ] x PRX_BLOCK doubles of dynamic shared memory
+  BdfCellT<BdfStoreLocalHot<PRX_BLOCK, PRX_SMEM_SRC>, CellSrcCol<PRX_BLOCK>> s;
+  s.src.rYsrc.p = prx_dyn_smem + threadIdx.x;
+  s.hot = prx_dyn_smem + N * PRX_BLOCK + threadIdx.x;
 #else
   BdfCell s;
 #endif
@@ -751,7 +755,6 @@ struct SrcRef
   long long stride;
 };
 
-extern __shared__ double prx_dyn_smem[];
 
 #ifndef PRX_FULL_VARIANTS
 #define PRX_FULL_VARIANTS 0 // 1: also build the measured dead ends (bdf2 / bdf3 / bdf4, profiles/README.md) for A/B runs
@@ -2384,12 +2387,12 @@ cudaError_t launch_unflatten(
 // =====================================================================================
 // launchers
 // =====================================================================================
-int persistent_grid(const void* kernel, const int ncells, const int block = PRX_BLOCK)
+int persistent_grid(const void* kernel, const int ncells, const int block = PRX_BLOCK, const int dyn_smem = 0)
 {
   int dev = 0, sms = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) {
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, dyn_smem) != cudaSuccess || per_sm < 1) {
     per_sm = 1;
   }
   long long grid = (long long)sms * per_sm; // a multiple of the SM count: one full wave, persistent
@@ -2486,8 +2489,17 @@ cudaError_t launch_bdf(
 #endif
 #if PRX_HAVE_BDF1
   auto kern = PRX_CAT(bdf_kernel_, PRX_MECH_SUFFIX);
+#if PRX_SMEM_SRC
+  // the shared-memory columns of PRX_MINBLOCKS resident blocks (+ 1 KB per block reserved by the system) must fit the
+  // carve-out, the rest stays L1 for the thread-local state
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PRX_BDF1_SMEM_BYTES);
+  cudaFuncSetAttribute(
+    kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+    (int)((100LL * PRX_MINBLOCKS * (PRX_BDF1_SMEM_BYTES + 1024) + 228 * 1024 - 1) / (228 * 1024)) + 2);
+#else
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1); // state lives in L1-cached local memory
-  int grid = persistent_grid((const void*)kern, a.ncells);
+#endif
+  int grid = persistent_grid((const void*)kern, a.ncells, PRX_BLOCK, PRX_BDF1_SMEM_BYTES);
   if (sp.max_warps_per_sm > 0) { // optional cap on resident warps (fewer resident cells: smaller L2 footprint)
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -2499,7 +2511,7 @@ cudaError_t launch_bdf(
   if (e != cudaSuccess) {
     return e;
   }
-  kern<<<grid, PRX_BLOCK, 0, stream>>>(a, p, sp, queue, stats);
+  kern<<<grid, PRX_BLOCK, PRX_BDF1_SMEM_BYTES, stream>>>(a, p, sp, queue, stats);
   return cudaGetLastError();
 #elif PRX_HAVE_COOP
   return launch_bdfc<32>(a, p, sp, queue, stats, stream);

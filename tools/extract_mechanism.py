@@ -283,13 +283,20 @@ def parse_reactions(src, nreac):
                 else:
                     r["reversible"] = True
                     mm = re.match(
-                        r"^(Corr \* )?k_f \* exp\(-\((.*?)\)\) \* (?:\((refC|refCinv|refC \* refC|refCinv \* refCinv)\) \* )?\((.*)\)$",
+                        r"^(Corr \* )?k_f \* exp\(-\((.*?)\)\) \* (?:\(+(refC|refCinv|refC \* refC|refCinv \* refCinv)\)+ \* )?\((.*)\)$",
                         rhs1)
                     assert mm, rhs1
+                    assert "refC" not in mm.group(4), rhs1  # |delta n| = 2 is printed with doubled parentheses
                     r["dG"] = parse_dg(mm.group(2))
                     r["refC"] = {None: 0, "refC": 1, "refCinv": -1, "refC * refC": 2,
                                  "refCinv * refCinv": -2}[mm.group(3)]
                     r["products"] = parse_sc_product(mm.group(4))
+                    if mm.group(4).strip() in ("0.0", "0"):
+                        # irreversible third-body / falloff reactions are printed as "... * (0.0)": no reverse rate
+                        r["reversible"] = False
+                        r["products"] = []
+                        r["dG"] = []
+                        r["refC"] = 0
             elif lhs.startswith("wdot["):
                 k = int(lhs[5:-1])
                 mm = re.match(r"^(?:(" + NUM + r") \* )?qdot$", rhs1)
