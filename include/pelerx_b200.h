@@ -236,7 +236,9 @@ PRX_API int prx_transport_boxes(
  * cells of ONE call as one coupled ODE system (one step size, one WRMS norm over all cells); this library integrates every
  * cell as its own system - the semantics of the reference's Array4 CPU path (ReactorCvode.cpp:1383-1464) - so results
  * coincide with the reference's for ncells = 1 and agree within the integrator tolerance otherwise.  The value the
- * reference returns from this call (nfe + nfeLS) is prx_last_react_return(): the largest per-cell count of the call. */
+ * reference returns from this call (nfe + nfeLS) is prx_last_react_return(): the largest per-cell count of the call.
+ * ReactorArkode (ReactorArkode.cpp:266-380): the ncells cells of the call are ONE coupled ERK system here as in the
+ * reference (one step size, one error norm); e advances by dt * esrc; prx_last_react_return() = nfe, also written to fc. */
 PRX_API int prx_react_flat(
   prx_handle* h, double* y, const double* ysrc, double* e, const double* esrc, double* fc,
   double dt, double time, int ncells, void* cuda_stream);

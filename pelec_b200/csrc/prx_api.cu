@@ -551,6 +551,45 @@ static int react_args(prx_handle* h, const BoxArgs& a, cudaStream_t stream)
   return PRX_OK;
 }
 
+// ---- ReactorArkode's 1-D react (ReactorArkode.cpp:266-380): the caller's cell-major vectors go into the integrator's CYOrder
+// columns as they are (no initial temperature solve: T is component N of each cell), and come back the same way; the energy
+// is advanced by its external source.
+__global__ void ark_flat_in_kernel(
+  const int nc, const int N, const double* __restrict__ y, const double* __restrict__ ysrc, const double* __restrict__ e,
+  const double* __restrict__ esrc, double* __restrict__ yn, double* __restrict__ rYsrc, double* __restrict__ rhoe,
+  double* __restrict__ rhoesrc)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) {
+    return;
+  }
+  for (int k = 0; k <= N; k++) {
+    yn[(long long)k * nc + c] = y[(long long)c * (N + 1) + k];
+  }
+  for (int k = 0; k < N; k++) {
+    rYsrc[(long long)k * nc + c] = ysrc[(long long)c * N + k];
+  }
+  rhoe[c] = e[c];
+  rhoesrc[c] = esrc[c];
+}
+
+__global__ void ark_flat_out_kernel(
+  const int nc, const int N, const double dt, const double* __restrict__ yn, const double* __restrict__ esrc,
+  double* __restrict__ y, double* __restrict__ e, double* __restrict__ fc, const double nfe)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) {
+    return;
+  }
+  for (int k = 0; k <= N; k++) {
+    y[(long long)c * (N + 1) + k] = yn[(long long)k * nc + c];
+  }
+  e[c] = e[c] + dt * esrc[c];
+  if (fc != nullptr) {
+    fc[c] = nfe;
+  }
+}
+
 // ---- ReactorArkode::react, Array4 (PP/Source/Reactions/ReactorArkode.cpp:135-260): see prx_arkode.cuh ---------------------
 static int react_arkode(prx_handle* h, const BoxArgs& a, cudaStream_t stream)
 {
@@ -626,7 +665,12 @@ static int react_arkode(prx_handle* h, const BoxArgs& a, cudaStream_t stream)
     }
     ARK_CUDA(cudaMemcpyAsync(atolv, atol_h.data(), neq * sizeof(double), cudaMemcpyHostToDevice, stream));
     // flatten (CYOrder), incl. the initial T solve of box_flatten
-    ARK_CUDA(ops->flatten(a, h->cfg, 1, yn, rYsrc, rhoe, rhoesrc, stream));
+    if (a.layout == LAYOUT_FLAT) {
+      ark_flat_in_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, stream>>>((int)nc, N, a.y, a.ysrc, a.e, a.esrc, yn, rYsrc, rhoe, rhoesrc);
+      ARK_CUDA(cudaGetLastError());
+    } else {
+      ARK_CUDA(ops->flatten(a, h->cfg, 1, yn, rYsrc, rhoe, rhoesrc, stream));
+    }
     const double t0 = a.time, tout = a.time + a.dt;
     double tn = t0, tcur = t0;
     // ---- arkInitialSetup: error weights, f(t0, y0), initial step
@@ -866,9 +910,14 @@ static int react_arkode(prx_handle* h, const BoxArgs& a, cudaStream_t stream)
       break;
     }
     // unflatten with FC = nfe in every cell (ReactorArkode.cpp:237-241); react returns nfe
-    ark::fill_ll_kernel<<<ark::RG, ark::RB, 0, stream>>>(nc, nfe, fcunt);
-    BoxArgs b = a;
-    ARK_CUDA(ops->unflatten(b, h->cfg, 1, yn, rhoe, fcunt, stream));
+    if (a.layout == LAYOUT_FLAT) {
+      ark_flat_out_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, stream>>>((int)nc, N, a.dt, yn, a.esrc, a.y, a.e, a.fc, (double)nfe);
+      ARK_CUDA(cudaGetLastError());
+    } else {
+      ark::fill_ll_kernel<<<ark::RG, ark::RB, 0, stream>>>(nc, nfe, fcunt);
+      BoxArgs b = a;
+      ARK_CUDA(ops->unflatten(b, h->cfg, 1, yn, rhoe, fcunt, stream));
+    }
     h->ark_last_nfe = nfe;
     h->ark_nfe += nfe;
     h->ark_cells += nc;
@@ -1322,9 +1371,6 @@ int prx_react_flat(
   if (y == nullptr || ysrc == nullptr || e == nullptr || esrc == nullptr) {
     return fail(h, PRX_ERR_BAD_ARG, "prx_react_flat: null pointer");
   }
-  if (h->cfg.reactor_kind == PRX_REACTOR_ARKODE) {
-    return fail(h, PRX_ERR_UNSUPPORTED, "prx_react_flat: the 1-D react of ReactorArkode is not implemented (Array4 react only)");
-  }
   BoxArgs a;
   std::memset(&a, 0, sizeof(a));
   a.layout = LAYOUT_FLAT;
@@ -1338,6 +1384,9 @@ int prx_react_flat(
   a.fc = fc;
   a.dt = dt;
   a.time = time;
+  if (h->cfg.reactor_kind == PRX_REACTOR_ARKODE) {
+    return react_arkode(h, a, (cudaStream_t)cuda_stream); // ReactorArkode.cpp:266-380; prx_last_react_return() = nfe
+  }
   return react_args(h, a, (cudaStream_t)cuda_stream);
 }
 

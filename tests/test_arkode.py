@@ -62,3 +62,35 @@ def test_arkode_unsupported_options_fail_loudly():
     r = ReactorB200.create("ReactorArkode", "LiDryer", ode__rk_controller=3)  # explicit Gustafsson
     with pytest.raises(PrxError):
         r.init(1, 1)
+
+
+@pytest.mark.parametrize("mech", ["LiDryer", "drm19"])
+def test_arkode_flat_react_matches_array4_fixture(mech):
+    """ReactorArkode's 1-D react (ReactorArkode.cpp:266-380) runs the same box-coupled integration on cell-major vectors whose
+    temperature component is taken as given.  The fixture's states carry T consistent with (rho e, rho Y), so the first call of
+    the Array4 fixture is the known answer: same number of right-hand-side evaluations (react's return value), rho Y and T to
+    the Array4 test's bar (the Array4 path re-solves T from the energy at both ends, the 1-D path returns the integrated T:
+    compared to 1e-9), rho e advanced by its source."""
+    from pelec_b200.reactor import ReactorB200
+    z = np.load(os.path.join(GOLD, "arkode_%s.npz" % mech))
+    kw = CASES["default"]
+    dt = float(z["dt"])
+    r = ReactorB200.create("ReactorArkode", mech, ode__rtol=kw["rtol"], ode__atol=kw["atol"], ode__rk_method=kw["rk_method"],
+                           ode__rk_controller=kw["rk_controller"])
+    r.init(1, 1)
+    pre = "default_0_"
+    rY0, T0, rE0, rYsrc, rEsrc = (z[pre + k] for k in ("rY0", "T0", "rE0", "rYsrc", "rEsrc"))
+    N, nc = rY0.shape
+    y = np.ascontiguousarray(np.concatenate([rY0, T0[None, :]], axis=0).T)  # [cell][N + 1]
+    ysrc = np.ascontiguousarray(rYsrc.T)
+    e, esrc, fc = rE0.copy(), rEsrc.copy(), np.zeros(nc)
+    r.react_flat_host(y, ysrc, e, esrc, dt, 0.0, nc, fc=fc)
+    nfe = int(z["default_nfe"][0])
+    assert r.last_react_return() == nfe and np.all(fc == nfe)
+    lim = kw["atol"] + kw["rtol"] * np.abs(z[pre + "rY"])
+    dy = float((np.abs(y[:, :N].T - z[pre + "rY"]) / lim).max())
+    dT = float((np.abs(y[:, N] - z[pre + "T"]) / z[pre + "T"]).max())
+    print("arkode flat %s: |d rhoY| / tol %.2e, |dT|/T %.2e, nfe %d" % (mech, dy, dT, nfe))
+    assert dy <= 1e-3 and dT <= 1e-9
+    assert np.array_equal(e, rE0 + dt * rEsrc)
+    r.close()
