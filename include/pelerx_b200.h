@@ -84,8 +84,10 @@ typedef struct prx_config {
   int clean_init_massfrac;  /* ode.clean_init_massfrac (0) */
   int verbose;              /* ode.verbose */
   int device;               /* CUDA device ordinal, -1 = current device */
-  int ark_method;           /* ode.rk_method (ReactorArkode.cpp:26-88): 40 Zonneveld 5-3-4 (default), 20 Heun-Euler 2-1-2,
-                               30 Bogacki-Shampine 4-2-3 */
+  int ark_method;           /* ode.rk_method (ReactorArkode.cpp:25-90): 40 Zonneveld 5-3-4 (default), 20 Heun-Euler, 30 Bogacki-
+                               Shampine, 31 / 41 / 43 / 53 / 54 the ARK-L2SA explicit tables, 42 Sayfy-Aburub, 50 Cash-Karp,
+                               51 Fehlberg 6-4-5, 52 Dormand-Prince; 60 / 80 (order 6 / 8): PRX_ERR_UNSUPPORTED; any other
+                               value = the default table, as in the reference */
   int ark_controller;       /* ode.rk_controller (ReactorArkode.cpp:90-116): 0 PID (default), 1 PI, 2 I */
   int ark_use_erkstep;      /* ode.use_erkstep (ReactorArkode.cpp:13): 1 = ERKStep (default), 0 = ARKStep with the same explicit
                                table - the same algorithm with ARKODE's generic adaptivity constants (safety 0.96, growth 20)

@@ -289,8 +289,13 @@ int prx_create(const prx_config* cfg, prx_handle** out)
     if (!(cfg->rtol > 0.0) || !(cfg->atol > 0.0)) {
       return PRX_ERR_BAD_ARG;
     }
-    if (!ark::table_for(cfg->ark_method, &ark_tab) || cfg->ark_controller < 0 || cfg->ark_controller > 2) {
-      return PRX_ERR_UNSUPPORTED; // the other ERK tables / the explicit-Gustafsson controller of ReactorArkode.cpp:26-116
+    // ReactorArkode.cpp:25-90: 60 / 80 select the order-6 / order-8 tables (Verner 8-5-6, Fehlberg 13-7-8: not carried, their
+    // dense output needs the quintic Hermite interpolant), any other unknown value falls back to the default table
+    if (cfg->ark_method == 60 || cfg->ark_method == 80 || cfg->ark_controller < 0 || cfg->ark_controller > 2) {
+      return PRX_ERR_UNSUPPORTED; // + the explicit-Gustafsson controller of ReactorArkode.cpp:92-116
+    }
+    if (!ark::table_for(cfg->ark_method, &ark_tab)) {
+      ark::table_for(40, &ark_tab);
     }
   }
   if (cfg->reactor_type != 1 && cfg->reactor_type != 2) {
@@ -614,7 +619,7 @@ static int react_arkode(prx_handle* h, const BoxArgs& a, cudaStream_t stream)
   double* fold = yold + n;
   double* ewt = fold + n;
   double* tmp = ewt + n;
-  double* F[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  double* F[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   for (int sidx = 0; sidx < B.stages; sidx++) {
     F[sidx] = tmp + (size_t)(sidx + 1) * n;
   }
@@ -891,8 +896,21 @@ static int react_arkode(prx_handle* h, const BoxArgs& a, cudaStream_t stream)
         }
         fn_is_current = true;
         const double tau2 = tau * tau, tau3 = tau * tau2;
-        const int deg = B.q - 1 < 3 ? B.q - 1 : 3; // interp degree min(5, q - 1); the tables here have q <= 4
-        if (deg >= 3) {
+        const int deg = B.q - 1; // interp degree min(5, q - 1); the tables carried have q <= 5
+        if (deg >= 4) {
+          // quartic (arkode_interp.c:578-600): the cubic interpolant at tau = -1/3, one more right-hand side there (counted in
+          // nfe like the reference's step_fullrhs), then five terms
+          const double ta = -1.0 / 3.0, ta2 = ta * ta, ta3 = ta * ta2;
+          ark::interp_kernel<<<ark::RG, ark::RB, 0, stream>>>(
+            n, 3.0 * ta2 + 2.0 * ta3, 1.0 - 3.0 * ta2 - 2.0 * ta3, h_i * (ta2 + ta3), h_i * (ta + 2.0 * ta2 + ta3), yold, yn, fold,
+            F[0], ycur);
+          ARK_CUDA(rhs_at(tnew_i - h_i / 3.0, ycur, tmp));
+          const double tau4 = tau * tau3;
+          ark::interp5_kernel<<<ark::RG, ark::RB, 0, stream>>>(
+            n, -6.0 * tau2 - 16.0 * tau3 - 9.0 * tau4, 1.0 + 6.0 * tau2 + 16.0 * tau3 + 9.0 * tau4,
+            h_i * 0.25 * (-5.0 * tau2 - 14.0 * tau3 - 9.0 * tau4), h_i * (tau + 2.0 * tau2 + tau3),
+            h_i * 27.0 * 0.25 * (-tau4 - 2.0 * tau3 - tau2), yold, yn, fold, F[0], tmp, ycur);
+        } else if (deg >= 3) {
           ark::interp_kernel<<<ark::RG, ark::RB, 0, stream>>>(
             n, 3.0 * tau2 + 2.0 * tau3, 1.0 - 3.0 * tau2 - 2.0 * tau3, h_i * (tau2 + tau3), h_i * (tau + 2.0 * tau2 + tau3), yold,
             yn, fold, F[0], ycur);

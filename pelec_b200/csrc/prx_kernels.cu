@@ -2421,7 +2421,11 @@ cudaError_t launch_rk64(const BoxArgs& a, const prx_config& cfg, int* queue, Dev
   if (e != cudaSuccess) {
     return e;
   }
-  kern<<<grid, PRX_RK_BLOCK, 0, stream>>>(a, p, queue, stats);
+  // ReactorRK64 reacts every cell of the box: the reference never reads the mask (ReactorRK64.cpp:175).  load_cell would
+  // skip a masked cell without loading it, and the integrator would run on the lane's previous cell.
+  BoxArgs b = a;
+  b.mask.p = nullptr;
+  kern<<<grid, PRX_RK_BLOCK, 0, stream>>>(b, p, queue, stats);
   return cudaGetLastError();
 }
 

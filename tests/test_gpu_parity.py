@@ -480,7 +480,13 @@ def test_host_slab_pipeline_equals_single_launch(key, monkeypatch):
         assert np.all(ref.FC[ref.mask == -1] == 0.0) and np.all(ref.FC[ref.mask != -1] > 0)
         assert np.array_equal(ref.rY[:, ref.mask == -1], st0.rY[:, st0.mask == -1])
     else:
-        assert np.all(ref.FC > 0)
+        # every cell is reacted, and a masked cell gets what it gets without the mask
+        assert np.all(ref.FC > 0) and np.all(np.isfinite(ref.rY))
+        monkeypatch.setenv("PRX_HOST_SLABS", "1")
+        st = st0.copy()
+        st.mask[:] = 1
+        react_host(r, st, 1e-6, nx, ny, nz)
+        assert np.array_equal(st.rY, ref.rY) and np.array_equal(st.T, ref.T) and np.array_equal(st.FC, ref.FC)
     for st, rv in out[1:]:
         for name in ("rY", "T", "rE", "FC"):
             assert np.array_equal(getattr(st, name), getattr(ref, name)), name

@@ -8,12 +8,16 @@ import numpy as np
 from oracle.pyoracle import Oracle, Reference, reacteval_states, BoxState
 
 def table(method):
-    if method == 40:
-        s=5; A=np.zeros((5,5)); A[1,0]=.5; A[2,1]=.5; A[3,2]=1.; A[4,0]=5/32; A[4,1]=7/32; A[4,2]=13/32; A[4,3]=-1/32
-        b=np.array([1/6,1/3,1/3,1/6,0.]); d=np.array([-1/2,7/3,7/3,13/6,-16/3]); c=np.array([0,.5,.5,1.,.75]); q,p=4,3
-    else:
-        s=4; A=np.zeros((4,4)); A[1,0]=.5; A[2,1]=.75; A[3,0]=2/9; A[3,1]=1/3; A[3,2]=4/9
-        b=np.array([2/9,1/3,4/9,0.]); d=np.array([7/24,1/4,1/3,1/8]); c=np.array([0,.5,.75,1.]); q,p=3,2
+    """the Butcher table of ode.rk_method from pelec_b200/csrc/prx_ark_tables.inc (the product's generated tables)"""
+    import re
+    txt=open(os.path.join(os.path.dirname(os.path.abspath(__file__)),'..','pelec_b200','csrc','prx_ark_tables.inc')).read()
+    blk=re.search(r"case %d:.*?return true;"%method, txt, re.S).group(0)
+    s,q,p=[int(v) for v in re.search(r"T->stages = (\d+); T->q = (\d+); T->p = (\d+);",blk).groups()]
+    A=np.zeros((s,s)); b=np.zeros(s); d=np.zeros(s); c=np.zeros(s)
+    for m in re.finditer(r"T->(A\[(\d+)\]\[(\d+)\]|([bdc])\[(\d+)\]) = ([^;]*);", blk):
+        v=eval(m.group(6))
+        if m.group(2) is not None: A[int(m.group(2)),int(m.group(3))]=v
+        else: {"b":b,"d":d,"c":c}[m.group(4)][int(m.group(5))]=v
     return s,A,b,d,c,q,p
 
 class Ctl:
@@ -21,7 +25,9 @@ class Ctl:
         s.k1,s.k2,s.k3=(0.58,-0.21,0.1) if kind==0 else ((0.8,-0.31,0.0) if kind==1 else (1.0,0,0))
         s.bias=1.5; s.ep=s.epp=s.hp=s.hpp=1.0; s.first=0
     def est(s,h,p,dsm):
-        o=p+1; e1=max(s.bias*dsm,1e-10); e2=max(s.ep,1e-10); e3=max(s.epp,1e-10)
+        # SUNMAX(A,B) = A > B ? A : B: a NaN error norm (a stage left the physical range) gives TINY, as in the reference
+        smax=lambda a,b: a if a>b else b
+        o=p+1; e1=smax(s.bias*dsm,1e-10); e2=smax(s.ep,1e-10); e3=smax(s.epp,1e-10)
         if s.first<1: return h*e1**(-s.k1/o)
         if s.first<2: return h*e1**(-s.k1/o)*e2**(-s.k2/o)
         return h*e1**(-s.k1/o)*e2**(-s.k2/o)*e3**(-s.k3/o)
@@ -105,13 +111,34 @@ def arkode_box(orc, st, dt, ctl, rtol, atol, method, typ=None, log=None):
             tau=(tout-tcur)/h
             fn=F[s-1].copy() if stiff else f(tn,yn)
             t2=tau*tau; t3=tau*t2
-            if q-1>=3: yout=(3*t2+2*t3)*yold+(1-3*t2-2*t3)*yn+hi*(t2+t3)*fold+hi*(tau+2*t2+t3)*fn
+            if q-1>=4:
+                ta=-1.0/3.0; a2=ta*ta; a3=ta*a2
+                ya=(3*a2+2*a3)*yold+(1-3*a2-2*a3)*yn+hi*(a2+a3)*fold+hi*(ta+2*a2+a3)*fn
+                fa=f(tn-hi/3.0,ya); t4=tau*t3
+                yout=(-6*t2-16*t3-9*t4)*yold+(1+6*t2+16*t3+9*t4)*yn+hi*0.25*(-5*t2-14*t3-9*t4)*fold+hi*(tau+2*t2+t3)*fn+hi*27*0.25*(-t4-2*t3-t2)*fa
+            elif q-1>=3: yout=(3*t2+2*t3)*yold+(1-3*t2-2*t3)*yn+hi*(t2+t3)*fold+hi*(tau+2*t2+t3)*fn
             elif q-1==2: yout=t2*yold+(1-t2)*yn+hi*(t2+tau)*fn
             else: yout=-tau*yold+(1+tau)*yn
             yn=yout; break
     return yn, nfe[0], nst, netf
 
+def tables_fixture():
+    z=np.load('/root/repo/tests/golden/arkode_tables_LiDryer.npz')
+    so=os.dup(1); os.dup2(os.open(os.devnull,os.O_WRONLY),1)
+    orc=Oracle("LiDryer"); N=orc.N
+    for m in z["methods"]:
+        ctl=Ctl(0)
+        for i in range(3):
+            pre="in_%d_"%i; po="m%d_%d_"%(m,i)
+            st=BoxState(z[pre+"rY0"].copy(),z[pre+"T0"].copy(),z[pre+"rE0"].copy(),z[pre+"rYsrc"].copy(),z[pre+"rEsrc"].copy())
+            y,nfe,nst,netf=arkode_box(orc,st,float(z["dt"]),ctl,1e-6,1e-10,int(m))
+            lim=1e-10+1e-6*np.abs(z[po+"rY"])
+            dy=np.max(np.abs(y[:,:N].T-z[po+"rY"])/lim)
+            sys.stderr.write("rk_method %d call %d: nfe %d (ref %d) nst %d netf %d dy/tol %.3e\n"%(m,i,nfe,int(z["m%d_nfe"%m][i]),nst,netf,dy))
+
 if __name__=="__main__":
+    if sys.argv[1]=="tables":
+        tables_fixture(); sys.exit(0)
     mech=sys.argv[1]; tag=sys.argv[2]
     z=np.load('/root/repo/tests/golden/arkode_%s.npz'%mech)
     os.dup2(os.open(os.devnull,os.O_WRONLY),1)
