@@ -57,7 +57,7 @@ typedef enum {
   PRX_REACTOR_ARKODE = 2     /* "ReactorArkode" PP/Source/Reactions/ReactorArkode.cpp:135-260 (ode.use_erkstep = 1, the default, or 0):
                                 ARKODE's adaptive explicit Runge-Kutta stepper on the WHOLE BOX as one system - one step
                                 size and one WRMS error norm for all cells of a react call, as the reference does on every
-                                backend; FC = the box's RHS-evaluation count in every cell.  Array4 react only. */
+                                backend; FC = the box's RHS-evaluation count in every cell.  Array4 and 1-D react. */
 } prx_reactor_kind;
 
 /* cvode.solve_type (PP/Source/Reactions/ReactorCvode.cpp:507-934) */
@@ -86,8 +86,8 @@ typedef struct prx_config {
   int device;               /* CUDA device ordinal, -1 = current device */
   int ark_method;           /* ode.rk_method (ReactorArkode.cpp:25-90): 40 Zonneveld 5-3-4 (default), 20 Heun-Euler, 30 Bogacki-
                                Shampine, 31 / 41 / 43 / 53 / 54 the ARK-L2SA explicit tables, 42 Sayfy-Aburub, 50 Cash-Karp,
-                               51 Fehlberg 6-4-5, 52 Dormand-Prince; 60 / 80 (order 6 / 8): PRX_ERR_UNSUPPORTED; any other
-                               value = the default table, as in the reference */
+                               51 Fehlberg 6-4-5, 52 Dormand-Prince, 60 Verner 8-5-6, 80 Fehlberg 13-7-8; any other value =
+                               the default table, as in the reference */
   int ark_controller;       /* ode.rk_controller (ReactorArkode.cpp:90-116): 0 PID (default), 1 PI, 2 I */
   int ark_use_erkstep;      /* ode.use_erkstep (ReactorArkode.cpp:13): 1 = ERKStep (default), 0 = ARKStep with the same explicit
                                table - the same algorithm with ARKODE's generic adaptivity constants (safety 0.96, growth 20)
@@ -177,7 +177,8 @@ PRX_API int prx_react_boxes(
  *   I_R    reaction source term, out                      NUM_SPECIES + 2 components (species, rho*E, heat release)
  *   work   optional (NULL): the reactor's FC per cell     1 component
  *   ix     component indices of the state vector (PC/Source/IndexDefines.H:3-12)
- * Not supported: rotating-frame energy (pelec.do_rf; rotenrg = 0) and EB-covered boxes (the caller skips those, :151-158). */
+ * The reference's mask is 1 everywhere here (dummyMask, :178); EB-covered boxes are skipped by the caller (:151-158).  The
+ * rotating-frame energy of pelec.do_rf: prx_set_rotating_frame below. */
 typedef struct prx_state_index {
   int urho, umx, umy, umz, ueden, ueint, utemp, ufs, nvar;
 } prx_state_index;

@@ -289,10 +289,9 @@ int prx_create(const prx_config* cfg, prx_handle** out)
     if (!(cfg->rtol > 0.0) || !(cfg->atol > 0.0)) {
       return PRX_ERR_BAD_ARG;
     }
-    // ReactorArkode.cpp:25-90: 60 / 80 select the order-6 / order-8 tables (Verner 8-5-6, Fehlberg 13-7-8: not carried, their
-    // dense output needs the quintic Hermite interpolant), any other unknown value falls back to the default table
-    if (cfg->ark_method == 60 || cfg->ark_method == 80 || cfg->ark_controller < 0 || cfg->ark_controller > 2) {
-      return PRX_ERR_UNSUPPORTED; // + the explicit-Gustafsson controller of ReactorArkode.cpp:92-116
+    // ReactorArkode.cpp:25-90: an unknown ode.rk_method falls back to the default table
+    if (cfg->ark_controller < 0 || cfg->ark_controller > 2) {
+      return PRX_ERR_UNSUPPORTED; // the explicit-Gustafsson controller of ReactorArkode.cpp:92-116
     }
     if (!ark::table_for(cfg->ark_method, &ark_tab)) {
       ark::table_for(40, &ark_tab);
@@ -619,7 +618,7 @@ static int react_arkode(prx_handle* h, const BoxArgs& a, cudaStream_t stream)
   double* fold = yold + n;
   double* ewt = fold + n;
   double* tmp = ewt + n;
-  double* F[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double* F[13] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   for (int sidx = 0; sidx < B.stages; sidx++) {
     F[sidx] = tmp + (size_t)(sidx + 1) * n;
   }
@@ -896,8 +895,33 @@ static int react_arkode(prx_handle* h, const BoxArgs& a, cudaStream_t stream)
         }
         fn_is_current = true;
         const double tau2 = tau * tau, tau3 = tau * tau2;
-        const int deg = B.q - 1; // interp degree min(5, q - 1); the tables carried have q <= 5
-        if (deg >= 4) {
+        const int deg = B.q - 1 < 5 ? B.q - 1 : 5; // interp degree min(5, q - 1)
+        if (deg >= 5) {
+          // quintic (arkode_interp.c:648-690).  The reference evaluates the quartic interpolant at tau = -1/3 and the right-hand
+          // side there, then the quartic at tau = -2/3 and the right-hand side there (fb); each quartic evaluation first
+          // evaluates the cubic at tau = -1/3 and stores ITS right-hand side in fa - so the fa of the final formula is f at
+          // the cubic's point, and f at the quartic's -1/3 point is computed, counted and overwritten.  Four right-hand sides
+          // are counted; the two whose results the reference discards are not launched.
+          const double ta = -1.0 / 3.0, ta2 = ta * ta, ta3 = ta * ta2;
+          ark::interp_kernel<<<ark::RG, ark::RB, 0, stream>>>(
+            n, 3.0 * ta2 + 2.0 * ta3, 1.0 - 3.0 * ta2 - 2.0 * ta3, h_i * (ta2 + ta3), h_i * (ta + 2.0 * ta2 + ta3), yold, yn, fold,
+            F[0], ycur);
+          ARK_CUDA(rhs_at(tnew_i - h_i / 3.0, ycur, tmp)); // fa
+          nfe += 2;                                         // the discarded pair (cubic point again, quartic(-1/3) point)
+          const double tb = -2.0 / 3.0, tb2 = tb * tb, tb3 = tb * tb2, tb4 = tb * tb3;
+          ark::interp5_kernel<<<ark::RG, ark::RB, 0, stream>>>(
+            n, -6.0 * tb2 - 16.0 * tb3 - 9.0 * tb4, 1.0 + 6.0 * tb2 + 16.0 * tb3 + 9.0 * tb4,
+            h_i * 0.25 * (-5.0 * tb2 - 14.0 * tb3 - 9.0 * tb4), h_i * (tb + 2.0 * tb2 + tb3),
+            h_i * 27.0 * 0.25 * (-tb4 - 2.0 * tb3 - tb2), yold, yn, fold, F[0], tmp, ycur);
+          ARK_CUDA(rhs_at(tnew_i - h_i * 2.0 / 3.0, ycur, F[1])); // fb (the stage vectors are free after the step)
+          const double tau4 = tau * tau3, tau5 = tau * tau4;
+          const double a0 = 54.0 * tau5 + 135.0 * tau4 + 110.0 * tau3 + 30.0 * tau2;
+          ark::interp6_kernel<<<ark::RG, ark::RB, 0, stream>>>(
+            n, a0, 1.0 - a0, h_i / 4.0 * (27.0 * tau5 + 63.0 * tau4 + 49.0 * tau3 + 13.0 * tau2),
+            h_i / 4.0 * (27.0 * tau5 + 72.0 * tau4 + 67.0 * tau3 + 26.0 * tau2 + 4.0 * tau),
+            h_i / 4.0 * (81.0 * tau5 + 189.0 * tau4 + 135.0 * tau3 + 27.0 * tau2),
+            h_i / 4.0 * (81.0 * tau5 + 216.0 * tau4 + 189.0 * tau3 + 54.0 * tau2), yold, yn, fold, F[0], tmp, F[1], ycur);
+        } else if (deg >= 4) {
           // quartic (arkode_interp.c:578-600): the cubic interpolant at tau = -1/3, one more right-hand side there (counted in
           // nfe like the reference's step_fullrhs), then five terms
           const double ta = -1.0 / 3.0, ta2 = ta * ta, ta3 = ta * ta2;

@@ -83,8 +83,8 @@ struct ArkStageArgs
 {
   int ncells, reactor_type, nterms;
   double t;
-  double coef[8];
-  const double* F[8];
+  double coef[13];
+  const double* F[13];
   const double* yn;
   double* ycur; // may be nullptr when nterms == 0 (f at yn itself)
   double* fout;

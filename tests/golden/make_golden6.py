@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Generate tests/golden/arkode_tables_LiDryer.npz from the UNMODIFIED reference's ReactorArkode (oracle/_ref/libpeleref_LiDryer.so;
-build container only): every other explicit Butcher table ode.rk_method selects up to order 5 (ReactorArkode.cpp:25-90 -
-31, 41, 42, 43: order 3 / 4, cubic Hermite dense output; 50 - 54: order 5, quartic dense output with its extra right-hand side),
+build container only): every other explicit Butcher table ode.rk_method selects (ReactorArkode.cpp:25-90 -
+31, 41, 42, 43: order 3 / 4, cubic Hermite dense output; 50 - 54: order 5, quartic dense output with its extra right-hand side;
+60, 80: order 6 / 8, quintic dense output with four more),
 ERKStep defaults (PID controller, rtol 1e-6, atol 1e-10), three successive react calls of ONE reactor object on the boxes of
 make_golden5.py (the controller's history carries over).  Inputs are stored once."""
 import os
@@ -15,7 +16,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 from make_golden5 import DT, boxes  # noqa: E402
 
-METHODS = (31, 41, 42, 43, 50, 51, 52, 53, 54)
+METHODS = (31, 41, 42, 43, 50, 51, 52, 53, 54, 60, 80)
 
 
 def main():

@@ -56,12 +56,26 @@ def test_arkode_matches_reference_over_successive_calls(mech, tag):
 
 def test_arkode_unsupported_options_fail_loudly():
     from pelec_b200.reactor import PrxError, ReactorB200
-    r = ReactorB200.create("ReactorArkode", "LiDryer", ode__rk_method=60)  # Verner 8-5-6 (order 6 needs the quintic dense output): not carried
-    with pytest.raises(PrxError):
-        r.init(1, 1)
     r = ReactorB200.create("ReactorArkode", "LiDryer", ode__rk_controller=3)  # explicit Gustafsson
     with pytest.raises(PrxError):
         r.init(1, 1)
+
+
+def test_arkode_unknown_method_is_the_default_table():
+    """ReactorArkode.cpp:86-89: an ode.rk_method outside the list selects Zonneveld 5-3-4"""
+    from oracle.pyoracle import BoxState
+    from pelec_b200.reactor import ReactorB200
+    z = np.load(os.path.join(GOLD, "arkode_LiDryer.npz"))
+    out = []
+    for method in (40, 99):
+        r = ReactorB200.create("ReactorArkode", "LiDryer", ode__rtol=1e-6, ode__atol=1e-10, ode__rk_method=method)
+        r.init(1, 1)
+        pre = "default_0_"
+        s = BoxState(z[pre + "rY0"].copy(), z[pre + "T0"].copy(), z[pre + "rE0"].copy(), z[pre + "rYsrc"].copy(), z[pre + "rEsrc"].copy())
+        r.react_host(s.ncells, 1, 1, s.rY, s.rYsrc, s.T, s.rE, s.rEsrc, s.FC, s.mask, float(z["dt"]), 0.0)
+        out.append((s.rY.copy(), s.T.copy(), r.last_react_return()))
+        r.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and out[0][2] == out[1][2]
 
 
 @pytest.mark.parametrize("mech", ["LiDryer", "drm19"])
@@ -96,11 +110,12 @@ def test_arkode_flat_react_matches_array4_fixture(mech):
     r.close()
 
 
-@pytest.mark.parametrize("method", [31, 41, 42, 43, 50, 51, 52, 53, 54])
+@pytest.mark.parametrize("method", [31, 41, 42, 43, 50, 51, 52, 53, 54, 60, 80])
 def test_arkode_other_butcher_tables_match_reference(method):
-    """Every other explicit table ode.rk_method selects up to order 5 (ReactorArkode.cpp:25-90; tables generated from SUNDIALS'
-    definitions by tools/extract_erk_tables.py).  Order-5 tables interpolate back to tout with ARKODE's quartic Hermite
-    polynomial, which costs one more right-hand side (arkode_interp.c:578-600) - part of the count compared here.  Table 43's
+    """Every other explicit table ode.rk_method selects (ReactorArkode.cpp:25-90; tables generated from SUNDIALS' definitions by
+    tools/extract_erk_tables.py).  Order-5 tables interpolate back to tout with ARKODE's quartic Hermite polynomial, which costs
+    one more right-hand side (arkode_interp.c:578-600), the order-6 / 8 tables (60: Verner 8-5-6, 80: Fehlberg 13-7-8) with the
+    quintic one, which costs four (:648-690) - part of the count compared here.  Table 43's
     first and third call run into stages outside the physical range (NaN error norm): the reference's controller treats the
     NaN as a tiny error and the error test as failed; the same sequence of RHS evaluations is the test.
     Fixture: tests/golden/make_golden6.py (unmodified reference, three successive calls of one reactor object)."""

@@ -111,7 +111,18 @@ def arkode_box(orc, st, dt, ctl, rtol, atol, method, typ=None, log=None):
             tau=(tout-tcur)/h
             fn=F[s-1].copy() if stiff else f(tn,yn)
             t2=tau*tau; t3=tau*t2
-            if q-1>=4:
+            if q-1>=5:
+                # quintic (arkode_interp.c case 5): fa = f at the CUBIC's -1/3 point (the nested quartic evaluations leave it there),
+                # fb = f at the quartic's -2/3 point; two more evaluations are made and discarded by the reference (counted)
+                ta=-1.0/3.0; a2=ta*ta; a3=ta*a2
+                ya=(3*a2+2*a3)*yold+(1-3*a2-2*a3)*yn+hi*(a2+a3)*fold+hi*(ta+2*a2+a3)*fn
+                fa=f(tn-hi/3.0,ya); nfe[0]+=2
+                tb=-2.0/3.0; b2=tb*tb; b3=tb*b2; b4=tb*b3
+                yb=(-6*b2-16*b3-9*b4)*yold+(1+6*b2+16*b3+9*b4)*yn+hi*0.25*(-5*b2-14*b3-9*b4)*fold+hi*(tb+2*b2+b3)*fn+hi*27*0.25*(-b4-2*b3-b2)*fa
+                fb=f(tn-hi*2.0/3.0,yb); t4=tau*t3; t5=tau*t4
+                a0=54*t5+135*t4+110*t3+30*t2
+                yout=a0*yold+(1-a0)*yn+hi/4*(27*t5+63*t4+49*t3+13*t2)*fold+hi/4*(27*t5+72*t4+67*t3+26*t2+4*tau)*fn+hi/4*(81*t5+189*t4+135*t3+27*t2)*fa+hi/4*(81*t5+216*t4+189*t3+54*t2)*fb
+            elif q-1>=4:
                 ta=-1.0/3.0; a2=ta*ta; a3=ta*a2
                 ya=(3*a2+2*a3)*yold+(1-3*a2-2*a3)*yn+hi*(a2+a3)*fold+hi*(ta+2*a2+a3)*fn
                 fa=f(tn-hi/3.0,ya); t4=tau*t3
